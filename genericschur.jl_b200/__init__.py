@@ -1,0 +1,323 @@
+"""Host-side mirror of GenericSchur.jl's interface for the Schur hot path, over libgschur_cuda (B200, sm_100a).
+
+The reference's host language (Julia) is not available in this environment; its shim is julia/GenericSchurCUDA.jl
+(see INTEGRATION.md).  This module is the same thin layer in Python, over the same C ABI, with the reference's
+names, argument meaning and error behaviour:
+
+  gschur(A; wantZ, scale, maxiter)      src/GenericSchur.jl:343      (copying)
+  gschur_(A; ...)                       gschur!  src/GenericSchur.jl:350-372, 805-835   (A is overwritten by T)
+  schur / schur_                        LinearAlgebra.schur!  src/pirates.jl:8-10
+  eigvals / eigvals_                    LinearAlgebra.eigvals! src/pirates.jl:17-27  (wantZ=false + sorteig!)
+  hessenberg / hessenberg_              LinearAlgebra.hessenberg! src/pirates.jl:232 -> _hessenberg! src/hessenberg.jl:3-17
+  gschur_hess_(H, Z)                    gschur!(H::Hessenberg, Z) src/GenericSchur.jl:194-335, 513-699
+  Schur(T, Z, values)                   LinearAlgebra.Schur{Ty,S,C}  (fields T, Z / vectors, values)
+  UnconvergedException                  src/GenericSchur.jl:39-45
+
+Array layout is Julia's: column-major.  A single matrix is an (n, n) Fortran-ordered ndarray; a batch is
+(n, n, batch) Fortran-ordered (`Array{T,3}`).  Element kinds:
+  float64 (n, n[, batch])                   Float64
+  complex128 (n, n[, batch])                ComplexF64
+  float64 (2, n, n[, batch]) via DD(...)    double-double, limbs (hi, lo)
+  float64 (4, n, n[, batch]) via CDD(...)   Complex{double-double}, (re.hi, re.lo, im.hi, im.lo)
+Everything executes on the GPU; there is no CPU fallback.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import C64, CDD, DD, F64
+
+__all__ = [
+    "gschur", "gschur_", "gschur_batched_", "schur", "schur_", "eigvals", "eigvals_", "hessenberg", "hessenberg_",
+    "gschur_hess_", "gschur_device_", "Schur", "Hessenberg", "UnconvergedException", "DimensionMismatch",
+    "ArgumentError", "DDArray", "CDDArray", "F64", "C64", "DD", "CDD", "device_count", "launch_count",
+]
+
+
+class UnconvergedException(Exception):
+    """Mirror of GenericSchur.UnconvergedException (src/GenericSchur.jl:39-45)."""
+
+
+class DimensionMismatch(ValueError):
+    """Mirror of Julia's DimensionMismatch (checksquare, src/GenericSchur.jl:354,811; :523-525)."""
+
+
+class ArgumentError(ValueError):
+    """Mirror of Julia's ArgumentError (src/GenericSchur.jl:206-210)."""
+
+
+class DDArray(np.ndarray):
+    """float64 array whose leading axis of length 2 holds (hi, lo) limbs of double-double numbers."""
+
+
+class CDDArray(np.ndarray):
+    """float64 array whose leading axis of length 4 holds (re.hi, re.lo, im.hi, im.lo)."""
+
+
+def _as_dd(x):
+    return np.asfortranarray(x, dtype=np.float64).view(DDArray)
+
+
+def _as_cdd(x):
+    return np.asfortranarray(x, dtype=np.float64).view(CDDArray)
+
+
+class Schur:
+    """LinearAlgebra.Schur: A = Z * T * Z'.  `values` pairs with diag(T).  Batched results carry a trailing axis."""
+
+    def __init__(self, T, Z, values, info=None, stats=None):
+        self.T = T
+        self.Z = Z
+        self.values = values
+        self.info = info
+        self.stats = stats
+
+    @property
+    def vectors(self):
+        return self.Z
+
+    @property
+    def Schur(self):
+        return self.T
+
+    def __iter__(self):   # destructuring: T, Z, values = schur(A)
+        return iter((self.T, self.Z, self.values))
+
+
+class Hessenberg:
+    """Result of hessenberg!: `factors` holds H on/above the sub-diagonal and the reflector tails below
+    (H.H.data === A in the reference, src/hessenberg.jl:16), `tau` the reflector scalars, `Q` the explicit
+    unitary factor (_materializeQ, src/hessenberg.jl:150-166)."""
+
+    def __init__(self, factors, tau, Q):
+        self.factors = factors
+        self.tau = tau
+        self.Q = Q
+
+    @property
+    def H(self):
+        n = self.factors.shape[-2 if self.factors.ndim % 2 == 0 or self.factors.ndim == 2 else -3]
+        F = np.array(self.factors, copy=True, order="F")
+        if F.ndim == 2:
+            return np.triu(F, -1)
+        raise NotImplementedError("H view is provided for single f64/c64 matrices; use factors otherwise")
+
+
+def device_count():
+    return _lib.lib().gschur_cuda_device_count()
+
+
+def launch_count():
+    return int(_lib.lib().gschur_cuda_launch_count())
+
+
+def max_batched_n(kind):
+    return _lib.lib().gschur_cuda_max_batched_n(kind)
+
+
+# ----------------------------------------------------------------------------------------------------------
+def _kind_and_shape(A):
+    """(kind, lead, n, batch or None) from an array in the layouts above; raises like the reference would."""
+    if isinstance(A, CDDArray):
+        kind, lead = CDD, 1
+    elif isinstance(A, DDArray):
+        kind, lead = DD, 1
+    elif A.dtype == np.complex128:
+        kind, lead = C64, 0
+    elif A.dtype == np.float64:
+        kind, lead = F64, 0
+    else:
+        # LinearAlgebra.schur! only has methods for T<:STypes (AbstractFloat / Complex{<:AbstractFloat}),
+        # src/GenericSchur.jl:24; test/errors.jl:16-28 expects a MethodError for Int / Rational.
+        raise TypeError(f"MethodError: no method matching gschur!(::Array{{{A.dtype}}})")
+    core = A.shape[lead:]
+    if lead and A.shape[0] != (2 if kind == DD else 4):
+        raise DimensionMismatch("leading limb axis has the wrong length")
+    if len(core) == 2:
+        m, n = core
+        batch = None
+    elif len(core) == 3:
+        m, n, batch = core
+    else:
+        raise DimensionMismatch(f"expected a matrix or a batch of matrices, got shape {A.shape}")
+    if m != n:
+        raise DimensionMismatch(f"matrix is not square: dimensions are ({m}, {n})")
+    return kind, lead, n, batch
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+
+
+def _check_rc(rc, maxiter, n):
+    if rc == 0:
+        return
+    msg = _lib.last_error()
+    if rc > 0:
+        raise UnconvergedException(f"iteration limit {maxiter if maxiter and maxiter > 0 else 100 * n} reached")
+    if rc == _lib.ERR_SUBDIAG:
+        raise ArgumentError("algorithm assumes real subdiagonal")
+    if rc == _lib.ERR_ARG and "DimensionMismatch" in msg:
+        raise DimensionMismatch(msg)
+    if rc == _lib.ERR_ARG:
+        raise ArgumentError(msg)
+    raise RuntimeError(f"libgschur_cuda error {rc}: {msg}")
+
+
+def _eig_array(kind, n, batch):
+    shape_b = () if batch is None else (batch,)
+    if kind in (F64, C64):
+        return np.zeros((n,) + shape_b, dtype=np.complex128, order="F")
+    return np.zeros((4, n) + shape_b, dtype=np.float64, order="F").view(CDDArray)
+
+
+def gschur_(A, wantZ=True, scale=True, maxiter=None, devices=None, check=True, flags=0, Z=None):
+    """gschur!(A; wantZ, scale, maxiter): A (Fortran-ordered, see module doc) is overwritten by T.
+
+    Works on one matrix or on a batch (trailing axis).  Returns Schur(T=A, Z, values[, info, stats]).
+    `devices`: list of CUDA device ordinals the batch is split over (contiguous slices, no collective).
+    """
+    kind, lead, n, batch = _kind_and_shape(A)
+    if not (A.flags.f_contiguous and A.flags.writeable):
+        raise ArgumentError("A must be a writeable Fortran-ordered (column-major) array")
+    nb = 1 if batch is None else batch
+    if wantZ:
+        if Z is None:
+            Z = np.zeros_like(A)
+        elif Z.shape != A.shape or Z.dtype != A.dtype or not Z.flags.f_contiguous:
+            raise DimensionMismatch("second dimension of Z must match H")
+    else:
+        Z = None
+    w = _eig_array(kind, n, batch)
+    info = np.zeros(nb, dtype=np.int32)
+    stats = np.zeros((_lib.STATS_PER_MATRIX, nb), dtype=np.uint32, order="F")
+    devs = None
+    ndev = 0
+    if devices is not None:
+        devs = (ctypes.c_int * len(devices))(*devices)
+        ndev = len(devices)
+    rc = _lib.lib().gschur_cuda_batched(
+        kind, n, nb, _ptr(A), n, n * n, _ptr(Z), n, n * n, _ptr(w), int(bool(scale)),
+        int(maxiter) if maxiter else 0, _ptr(info), _ptr(stats), devs, ndev, flags)
+    if check:
+        _check_rc(rc, maxiter, n)
+    if wantZ is False:
+        # the reference returns a 0x0 matrix when wantZ=false (src/GenericSchur.jl:334, 698)
+        Z = np.zeros((0, 0), dtype=A.dtype)
+    return Schur(A, Z, w, info=info if batch is not None else int(info[0]), stats=stats)
+
+
+gschur_batched_ = gschur_
+
+
+def _copy_f(A):
+    cls = type(A) if isinstance(A, (DDArray, CDDArray)) else None
+    B = np.array(A, order="F", copy=True)
+    return B.view(cls) if cls is not None else B
+
+
+def gschur(A, **kw):
+    """gschur(A) = gschur!(Matrix(A))  (src/GenericSchur.jl:343)."""
+    A = np.asarray(A) if not isinstance(A, np.ndarray) else A
+    _kind_and_shape(A)
+    return gschur_(_copy_f(A), **kw)
+
+
+def schur_(A, **kw):
+    """LinearAlgebra.schur!(A) for T<:STypes (src/pirates.jl:8-10)."""
+    return gschur_(A, **kw)
+
+
+def schur(A, **kw):
+    return gschur(A, **kw)
+
+
+def _sorteig(values, sortby):
+    """stdlib sorteig!: default eigsortby = λ -> (real(λ), imag(λ))."""
+    if sortby is None:
+        return values
+    if values.ndim == 1:
+        return np.array(sorted(values, key=sortby))
+    out = np.empty_like(values)
+    for b in range(values.shape[1]):
+        out[:, b] = sorted(values[:, b], key=sortby)
+    return out
+
+
+def eigsortby(lam):
+    return (lam.real, lam.imag)
+
+
+def eigvals_(A, sortby=eigsortby, **kw):
+    """LinearAlgebra.eigvals!(A; sortby) (src/pirates.jl:17-27): gschur!(A; wantZ=false) then sorteig!."""
+    S = gschur_(A, wantZ=False, **kw)
+    v = S.values
+    if isinstance(v, CDDArray):
+        return v   # double-double eigenvalues are returned unsorted limbs; sort on (hi) upstream if needed
+    return _sorteig(v, sortby)
+
+
+def eigvals(A, sortby=eigsortby, **kw):
+    A = np.asarray(A) if not isinstance(A, np.ndarray) else A
+    _kind_and_shape(A)
+    return eigvals_(_copy_f(A), sortby=sortby, **kw)
+
+
+def hessenberg_(A, wantQ=True, devices=None):
+    """hessenberg!(A) (src/pirates.jl:232 -> _hessenberg!, src/hessenberg.jl:3-17) and _materializeQ."""
+    kind, lead, n, batch = _kind_and_shape(A)
+    if not (A.flags.f_contiguous and A.flags.writeable):
+        raise ArgumentError("A must be a writeable Fortran-ordered (column-major) array")
+    nb = 1 if batch is None else batch
+    tshape = A.shape[:lead] + (max(n - 1, 0),) + (() if batch is None else (batch,))
+    tau = np.zeros(tshape, dtype=A.dtype, order="F")
+    if isinstance(A, (DDArray, CDDArray)):
+        tau = tau.view(type(A))
+    Q = np.zeros_like(A) if wantQ else None
+    devs = None
+    ndev = 0
+    if devices is not None:
+        devs = (ctypes.c_int * len(devices))(*devices)
+        ndev = len(devices)
+    rc = _lib.lib().gschur_cuda_hessenberg_batched(kind, n, nb, _ptr(A), n, n * n, _ptr(tau), _ptr(Q), n, n * n,
+                                                  devs, ndev, 0)
+    _check_rc(rc, None, n)
+    return Hessenberg(A, tau, Q)
+
+
+def hessenberg(A, **kw):
+    A = np.asarray(A) if not isinstance(A, np.ndarray) else A
+    _kind_and_shape(A)
+    return hessenberg_(_copy_f(A), **kw)
+
+
+def gschur_hess_(H, Z=None, maxiter=None, checksd=True):
+    """gschur!(H::Hessenberg, Z): H upper Hessenberg (overwritten by T), Z updated in place if given
+    (src/GenericSchur.jl:194-335 complex, 513-699 real).  Raises ArgumentError for a non-real sub-diagonal
+    (checksd) and DimensionMismatch when Z does not match (test/errors.jl:1-10)."""
+    kind, lead, n, batch = _kind_and_shape(H)
+    if Z is not None:
+        if Z.shape[lead + 1] != n or Z.shape != H.shape:
+            raise DimensionMismatch("second dimension of Z must match H")
+    flags = _lib.FLAG_HESS_INPUT | (_lib.FLAG_CHECK_SUBDIAG if checksd else 0)
+    return gschur_(H, wantZ=Z is not None, scale=False, maxiter=maxiter, flags=flags, Z=Z)
+
+
+def gschur_device_(kind, n, batch, A_ptr, Z_ptr, w_ptr, info_ptr=None, stats_ptr=None, scale=True, maxiter=0,
+                   stream=None, lda=None, strideA=None, ldz=None, strideZ=None):
+    """Device-resident, asynchronous gschur! over raw device pointers (e.g. torch tensors' data_ptr()) on the
+    current CUDA device; enqueued on `stream` (a cudaStream_t as int).  Used by bench.py for the HBM-resident
+    timing; convergence is reported through the info array only."""
+    lda = n if lda is None else lda
+    ldz = n if ldz is None else ldz
+    strideA = n * n if strideA is None else strideA
+    strideZ = n * n if strideZ is None else strideZ
+    rc = _lib.lib().gschur_cuda_batched_async(
+        kind, n, batch, ctypes.c_void_p(A_ptr), lda, strideA, ctypes.c_void_p(Z_ptr) if Z_ptr else None, ldz,
+        strideZ, ctypes.c_void_p(w_ptr), int(bool(scale)), int(maxiter),
+        ctypes.c_void_p(info_ptr) if info_ptr else None, ctypes.c_void_p(stats_ptr) if stats_ptr else None,
+        ctypes.c_void_p(stream) if stream else None, 0)
+    if rc != 0:
+        _check_rc(rc, maxiter, n)
+    return rc

@@ -1,0 +1,67 @@
+"""ctypes loader for libgschur_cuda.so (the C ABI declared in include/gschur_cuda.h).
+
+The library is built in-tree (genericschur.jl_b200/libgschur_cuda.so) by csrc/Makefile.  Loading fails loudly:
+there is no Python or CPU fallback for any entry point.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgschur_cuda.so")
+
+F64, C64, DD, CDD = 0, 1, 2, 3
+FLAG_DEVICE_PTRS = 0x1
+FLAG_HESS_INPUT = 0x2
+FLAG_CHECK_SUBDIAG = 0x4
+ERR_ARG, ERR_CUDA, ERR_SIZE, ERR_SUBDIAG = -1, -2, -3, -4
+STATS_PER_MATRIX = 4
+
+EXPORTS = [
+    "gschur_cuda_version",
+    "gschur_cuda_device_count",
+    "gschur_cuda_last_error",
+    "gschur_cuda_launch_count",
+    "gschur_cuda_max_batched_n",
+    "gschur_cuda_batched",
+    "gschur_cuda_batched_async",
+    "gschur_cuda_hessenberg_batched",
+]
+
+_lib = None
+
+
+def build(jobs=8):
+    """Compile the CUDA library for sm_100a with nvcc (works without a GPU)."""
+    subprocess.check_call(["make", "-s", "-j", str(jobs), "-C", os.path.join(_HERE, "csrc")])
+    return LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C genericschur.jl_b200/csrc -j` "
+                "(or __graft_entry__.build()). There is no CPU fallback."
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        vp, ci, i64, u32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32
+        L.gschur_cuda_version.restype = ci
+        L.gschur_cuda_device_count.restype = ci
+        L.gschur_cuda_last_error.restype = ctypes.c_char_p
+        L.gschur_cuda_launch_count.restype = ctypes.c_uint64
+        L.gschur_cuda_max_batched_n.argtypes = [ci]
+        L.gschur_cuda_max_batched_n.restype = ci
+        L.gschur_cuda_batched.argtypes = [ci, ci, i64, vp, ci, i64, vp, ci, i64, vp, ci, ci, vp, vp, vp, ci, u32]
+        L.gschur_cuda_batched.restype = ci
+        L.gschur_cuda_batched_async.argtypes = [ci, ci, i64, vp, ci, i64, vp, ci, i64, vp, ci, ci, vp, vp, vp, u32]
+        L.gschur_cuda_batched_async.restype = ci
+        L.gschur_cuda_hessenberg_batched.argtypes = [ci, ci, i64, vp, ci, i64, vp, vp, ci, i64, vp, ci, u32]
+        L.gschur_cuda_hessenberg_batched.restype = ci
+        _lib = L
+    return _lib
+
+
+def last_error():
+    return lib().gschur_cuda_last_error().decode()

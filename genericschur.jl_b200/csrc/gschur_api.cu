@@ -1,0 +1,457 @@
+// libgschur_cuda: C ABI (include/gschur_cuda.h) and host-side orchestration.
+//  - device-pointer entry: one persistent kernel launch per call on the caller's stream;
+//  - host-pointer entry: the batch is split in contiguous slices over the requested devices (one host
+//    thread per device, no collective), each slice is pipelined in chunks over three streams so that
+//    H2D, compute and D2H overlap.
+// There is no CPU fallback anywhere in this file.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/gschur_cuda.h"
+#include "launch.h"
+
+using namespace gs;
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (expr);                                                                   \
+        if (e__ != cudaSuccess)                                                                     \
+            return fail(GSCHUR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));      \
+    } while (0)
+
+size_t elem_size(int kind) { return kind == GSCHUR_F64 ? 8 : (kind == GSCHUR_CDD ? 32 : 16); }
+size_t eig_size(int kind) { return kind >= GSCHUR_DD ? 32 : 16; }
+
+constexpr size_t kMaxSmem = 232448;   // 227 KiB opt-in limit per CTA on sm_100
+
+int max_batched_n(int kind) {
+    static int cache[4] = {0, 0, 0, 0};
+    if (kind < 0 || kind > 3) return 0;
+    if (!cache[kind]) {
+        int n = 1;
+        while (gs::batched_smem_bytes(kind, n + 1) <= kMaxSmem) ++n;
+        cache[kind] = n;
+    }
+    return cache[kind];
+}
+
+// ---- per-device state: work-queue counters -------------------------------------------------------------
+struct DeviceState {
+    unsigned long long* counters = nullptr;   // ring of queue heads
+    std::atomic<unsigned> next{0};
+    int sm_count = 0;
+    bool ok = false;
+};
+constexpr int kCounterRing = 1024;
+constexpr int kMaxDevices = 64;
+DeviceState g_dev[kMaxDevices];
+std::mutex g_dev_mu;
+
+int device_state(int dev, DeviceState** out) {
+    if (dev < 0 || dev >= kMaxDevices) return fail(GSCHUR_ERR_ARG, "device index out of range");
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    DeviceState& d = g_dev[dev];
+    if (!d.ok) {
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+        if (prop.major != 10)
+            return fail(GSCHUR_ERR_CUDA, "libgschur_cuda is built for sm_100a only; device is sm_" +
+                                             std::to_string(prop.major) + std::to_string(prop.minor));
+        d.sm_count = prop.multiProcessorCount;
+        CUDA_TRY(cudaMalloc(&d.counters, kCounterRing * sizeof(unsigned long long)));
+        d.ok = true;
+    }
+    *out = &d;
+    return 0;
+}
+
+// ---- kernel launch: one translation unit per element kind (launch_<kind>.cu) ------------------------------
+int launch_kind(int kind, const BatchedParams& p, int dev_sms, cudaStream_t stream) {
+    std::string err;
+    int rc;
+    switch (kind) {
+        case GSCHUR_F64: rc = gs::launch_f64(p, dev_sms, stream, &err); break;
+        case GSCHUR_C64: rc = gs::launch_c64(p, dev_sms, stream, &err); break;
+        case GSCHUR_DD: rc = gs::launch_dd(p, dev_sms, stream, &err); break;
+        case GSCHUR_CDD: rc = gs::launch_cdd(p, dev_sms, stream, &err); break;
+        default: return fail(GSCHUR_ERR_ARG, "bad kind");
+    }
+    if (rc) return fail(rc, err);
+    g_launches.fetch_add(1);
+    return 0;
+}
+
+int check_args(int kind, int n, int64_t batch, const void* A, int lda, int64_t strideA, const void* Z, int ldz,
+               int64_t strideZ, const void* w) {
+    if (kind < 0 || kind > 3) return fail(GSCHUR_ERR_ARG, "kind must be 0..3");
+    if (n < 0 || batch < 0) return fail(GSCHUR_ERR_ARG, "n and batch must be non-negative");
+    if (n == 0 || batch == 0) return 0;
+    if (!A) return fail(GSCHUR_ERR_ARG, "A is NULL");
+    if (lda < n) return fail(GSCHUR_ERR_ARG, "DimensionMismatch: lda < n");
+    if (batch > 1 && strideA < (int64_t)lda * (n - 1) + n) return fail(GSCHUR_ERR_ARG, "strideA overlaps matrices");
+    if (Z) {
+        if (ldz < n) return fail(GSCHUR_ERR_ARG, "DimensionMismatch: ldz < n");
+        if (batch > 1 && strideZ < (int64_t)ldz * (n - 1) + n) return fail(GSCHUR_ERR_ARG, "strideZ overlaps matrices");
+    }
+    if (!w) return fail(GSCHUR_ERR_ARG, "w is NULL");
+    if (n > max_batched_n(kind))
+        return fail(GSCHUR_ERR_SIZE, "n = " + std::to_string(n) + " exceeds the batched-kernel limit " +
+                                         std::to_string(max_batched_n(kind)) + " for this kind");
+    return 0;
+}
+
+// enqueue one device-resident batch on `stream` of the current device
+int enqueue_device(int kind, int mode, int n, int64_t batch, void* A, int lda, int64_t strideA, void* Z, int ldz,
+                   int64_t strideZ, void* w, void* tau, int scale, int maxiter, int32_t* info, uint32_t* stats,
+                   cudaStream_t stream, uint32_t flags) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    DeviceState* ds = nullptr;
+    int rc = device_state(dev, &ds);
+    if (rc) return rc;
+    unsigned slot = ds->next.fetch_add(1) % kCounterRing;
+    unsigned long long* counter = ds->counters + slot;
+    CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
+    BatchedParams p;
+    p.A = A;
+    p.Z = Z;
+    p.w = w;
+    p.tau = tau;
+    p.strideA = strideA;
+    p.strideZ = strideZ;
+    p.batch = batch;
+    p.lda = lda;
+    p.ldz = ldz;
+    p.n = n;
+    p.scale = scale;
+    p.maxiter = maxiter;
+    p.mode = mode;
+    p.flags = flags & (GSCHUR_FLAG_HESS_INPUT | GSCHUR_FLAG_CHECK_SUBDIAG);
+    p.info = info;
+    p.stats = stats;
+    p.counter = counter;
+    return launch_kind(kind, p, ds->sm_count, stream);
+}
+
+// ---- host-pointer path: one worker per device, chunked 3-stream pipeline ---------------------------------
+struct HostJob {
+    int kind, mode, n, lda, ldz, scale, maxiter;
+    int64_t strideA, strideZ;
+    char *A, *Z, *w, *tau;
+    int32_t* info;
+    uint32_t* stats;
+    uint32_t flags;
+};
+
+struct ChunkBuf {
+    void *dA = nullptr, *dZ = nullptr, *dw = nullptr, *dtau = nullptr;
+    int32_t* dinfo = nullptr;
+    uint32_t* dstats = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* err) {
+#define SL_TRY(expr)                                                                  \
+    do {                                                                              \
+        cudaError_t e__ = (expr);                                                     \
+        if (e__ != cudaSuccess) {                                                     \
+            *err = std::string(#expr) + ": " + cudaGetErrorString(e__);               \
+            rc_final = GSCHUR_ERR_CUDA;                                               \
+            goto cleanup;                                                             \
+        }                                                                             \
+    } while (0)
+    int rc_final = 0;
+    const int n = J.n;
+    const size_t es = elem_size(J.kind), ws = eig_size(J.kind);
+    const size_t mat = (size_t)n * n * es;
+    const int64_t count = b1 - b0;
+    constexpr int NBUF = 3;
+    ChunkBuf buf[NBUF];
+    // chunk size: aim at >= 8 chunks per slice but at least enough matrices to fill the GPU a few times over
+    int64_t chunk = (count + 7) / 8;
+    const int64_t min_chunk = 2048;
+    if (chunk < min_chunk) chunk = min_chunk;
+    if (chunk > count) chunk = count;
+    const bool wantZ = J.Z != nullptr;
+    const bool hess = J.mode == MODE_HESSENBERG;
+    const bool zin = wantZ && (J.flags & GSCHUR_FLAG_HESS_INPUT) && !hess;
+    const bool denseA = (J.lda == n) && (J.strideA == (int64_t)n * n);
+    const bool denseZ = (J.ldz == n) && (J.strideZ == (int64_t)n * n);
+    if (cudaSetDevice(dev) != cudaSuccess) {
+        *err = "cudaSetDevice failed";
+        return GSCHUR_ERR_CUDA;
+    }
+    {
+        DeviceState* ds = nullptr;
+        int rc = device_state(dev, &ds);
+        if (rc) {
+            *err = g_err;
+            return rc;
+        }
+    }
+    for (int i = 0; i < NBUF; ++i) {
+        SL_TRY(cudaStreamCreateWithFlags(&buf[i].stream, cudaStreamNonBlocking));
+        SL_TRY(cudaMalloc(&buf[i].dA, mat * chunk));
+        if (wantZ) SL_TRY(cudaMalloc(&buf[i].dZ, mat * chunk));
+        if (!hess) SL_TRY(cudaMalloc(&buf[i].dw, ws * n * chunk));
+        if (hess) SL_TRY(cudaMalloc(&buf[i].dtau, es * (n > 1 ? n - 1 : 1) * chunk));
+        SL_TRY(cudaMalloc(&buf[i].dinfo, sizeof(int32_t) * chunk));
+        SL_TRY(cudaMalloc(&buf[i].dstats, sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX * chunk));
+    }
+    {
+        int ci = 0;
+        for (int64_t c0 = b0; c0 < b1; c0 += chunk, ++ci) {
+            ChunkBuf& B = buf[ci % NBUF];
+            const int64_t cn = (c0 + chunk <= b1) ? chunk : (b1 - c0);
+            cudaStream_t s = B.stream;
+            // H2D
+            if (denseA) {
+                SL_TRY(cudaMemcpyAsync(B.dA, J.A + (size_t)c0 * J.strideA * es, mat * cn, cudaMemcpyHostToDevice, s));
+            } else {
+                for (int64_t b = 0; b < cn; ++b)
+                    SL_TRY(cudaMemcpy2DAsync((char*)B.dA + b * mat, (size_t)n * es,
+                                             J.A + (size_t)(c0 + b) * J.strideA * es, (size_t)J.lda * es,
+                                             (size_t)n * es, n, cudaMemcpyHostToDevice, s));
+            }
+            if (zin) {
+                if (denseZ) {
+                    SL_TRY(cudaMemcpyAsync(B.dZ, J.Z + (size_t)c0 * J.strideZ * es, mat * cn, cudaMemcpyHostToDevice, s));
+                } else {
+                    for (int64_t b = 0; b < cn; ++b)
+                        SL_TRY(cudaMemcpy2DAsync((char*)B.dZ + b * mat, (size_t)n * es,
+                                                 J.Z + (size_t)(c0 + b) * J.strideZ * es, (size_t)J.ldz * es,
+                                                 (size_t)n * es, n, cudaMemcpyHostToDevice, s));
+                }
+            }
+            int rc = enqueue_device(J.kind, J.mode, n, cn, B.dA, n, (int64_t)n * n, wantZ ? B.dZ : nullptr, n,
+                                    (int64_t)n * n, B.dw, B.dtau, J.scale, J.maxiter, B.dinfo, B.dstats, s, J.flags);
+            if (rc) {
+                *err = g_err;
+                rc_final = rc;
+                goto cleanup;
+            }
+            // D2H
+            if (denseA) {
+                SL_TRY(cudaMemcpyAsync(J.A + (size_t)c0 * J.strideA * es, B.dA, mat * cn, cudaMemcpyDeviceToHost, s));
+            } else {
+                for (int64_t b = 0; b < cn; ++b)
+                    SL_TRY(cudaMemcpy2DAsync(J.A + (size_t)(c0 + b) * J.strideA * es, (size_t)J.lda * es,
+                                             (char*)B.dA + b * mat, (size_t)n * es, (size_t)n * es, n,
+                                             cudaMemcpyDeviceToHost, s));
+            }
+            if (wantZ) {
+                if (denseZ) {
+                    SL_TRY(cudaMemcpyAsync(J.Z + (size_t)c0 * J.strideZ * es, B.dZ, mat * cn, cudaMemcpyDeviceToHost, s));
+                } else {
+                    for (int64_t b = 0; b < cn; ++b)
+                        SL_TRY(cudaMemcpy2DAsync(J.Z + (size_t)(c0 + b) * J.strideZ * es, (size_t)J.ldz * es,
+                                                 (char*)B.dZ + b * mat, (size_t)n * es, (size_t)n * es, n,
+                                                 cudaMemcpyDeviceToHost, s));
+                }
+            }
+            if (!hess)
+                SL_TRY(cudaMemcpyAsync(J.w + (size_t)c0 * n * ws, B.dw, ws * n * cn, cudaMemcpyDeviceToHost, s));
+            if (hess && n > 1)
+                SL_TRY(cudaMemcpyAsync(J.tau + (size_t)c0 * (n - 1) * es, B.dtau, es * (n - 1) * cn,
+                                       cudaMemcpyDeviceToHost, s));
+            if (J.info && !hess)
+                SL_TRY(cudaMemcpyAsync(J.info + c0, B.dinfo, sizeof(int32_t) * cn, cudaMemcpyDeviceToHost, s));
+            if (J.stats && !hess)
+                SL_TRY(cudaMemcpyAsync(J.stats + (size_t)c0 * GSCHUR_STATS_PER_MATRIX, B.dstats,
+                                       sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX * cn, cudaMemcpyDeviceToHost, s));
+        }
+    }
+    for (int i = 0; i < NBUF; ++i) SL_TRY(cudaStreamSynchronize(buf[i].stream));
+cleanup:
+    for (int i = 0; i < NBUF; ++i) {
+        if (buf[i].stream) {
+            cudaStreamSynchronize(buf[i].stream);
+            cudaStreamDestroy(buf[i].stream);
+        }
+        cudaFree(buf[i].dA);
+        cudaFree(buf[i].dZ);
+        cudaFree(buf[i].dw);
+        cudaFree(buf[i].dtau);
+        cudaFree(buf[i].dinfo);
+        cudaFree(buf[i].dstats);
+    }
+    return rc_final;
+#undef SL_TRY
+}
+
+int run_host(const HostJob& J, int64_t batch, const int* devices, int ndev) {
+    int dev0 = 0;
+    std::vector<int> devs;
+    if (devices && ndev > 0) devs.assign(devices, devices + ndev);
+    else devs.push_back(dev0);
+    int have = 0;
+    CUDA_TRY(cudaGetDeviceCount(&have));
+    for (int d : devs)
+        if (d < 0 || d >= have) return fail(GSCHUR_ERR_ARG, "device " + std::to_string(d) + " not present");
+    const int G = (int)devs.size();
+    std::vector<int> rcs(G, 0);
+    std::vector<std::string> errs(G);
+    std::vector<std::thread> th;
+    // info is needed to count failures even when the caller passed NULL
+    std::vector<int32_t> info_local;
+    HostJob JJ = J;
+    if (!JJ.info && JJ.mode == MODE_SCHUR) {
+        info_local.assign((size_t)batch, 0);
+        JJ.info = info_local.data();
+    }
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int g = 0; g < G; ++g) {
+        int64_t b0 = batch * g / G, b1 = batch * (g + 1) / G;
+        if (b1 <= b0) continue;
+        if (G == 1) {
+            rcs[g] = run_slice(JJ, devs[g], b0, b1, &errs[g]);
+        } else {
+            th.emplace_back([&, g, b0, b1]() { rcs[g] = run_slice(JJ, devs[g], b0, b1, &errs[g]); });
+        }
+    }
+    for (auto& t : th) t.join();
+    cudaSetDevice(prev);
+    for (int g = 0; g < G; ++g)
+        if (rcs[g]) return fail(rcs[g], "device " + std::to_string(devs[g]) + ": " + errs[g]);
+    if (JJ.mode == MODE_SCHUR) {
+        int64_t bad = 0;
+        bool subdiag = false;
+        for (int64_t b = 0; b < batch; ++b) {
+            if (JJ.info[b] > 0) ++bad;
+            if (JJ.info[b] == GSCHUR_ERR_SUBDIAG) subdiag = true;
+        }
+        if (subdiag) return fail(GSCHUR_ERR_SUBDIAG, "ArgumentError: algorithm assumes real subdiagonal");
+        if (bad) g_err = "UnconvergedException: iteration limit reached for " + std::to_string(bad) + " matrices";
+        return (int)(bad > 0x7fffffff ? 0x7fffffff : bad);
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gschur_cuda_version(void) { return 100; }
+
+int gschur_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        g_err = "cudaGetDeviceCount failed (no CUDA device / driver)";
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char* gschur_cuda_last_error(void) { return g_err.c_str(); }
+
+uint64_t gschur_cuda_launch_count(void) { return g_launches.load(); }
+
+int gschur_cuda_max_batched_n(int kind) { return max_batched_n(kind); }
+
+int gschur_cuda_batched_async(int kind, int n, int64_t batch, void* A, int lda, int64_t strideA, void* Z, int ldz,
+                              int64_t strideZ, void* w, int scale, int maxiter, int32_t* info, uint32_t* stats,
+                              void* stream, uint32_t flags) {
+    g_err.clear();
+    int rc = check_args(kind, n, batch, A, lda, strideA, Z, ldz, strideZ, w);
+    if (rc) return rc;
+    if (n == 0 || batch == 0) return 0;
+    return enqueue_device(kind, MODE_SCHUR, n, batch, A, lda, strideA, Z, ldz, strideZ, w, nullptr, scale, maxiter,
+                          info, stats, (cudaStream_t)stream, flags);
+}
+
+int gschur_cuda_batched(int kind, int n, int64_t batch, void* A, int lda, int64_t strideA, void* Z, int ldz,
+                        int64_t strideZ, void* w, int scale, int maxiter, int32_t* info, uint32_t* stats,
+                        const int* devices, int ndev, uint32_t flags) {
+    g_err.clear();
+    int rc = check_args(kind, n, batch, A, lda, strideA, Z, ldz, strideZ, w);
+    if (rc) return rc;
+    if (n == 0 || batch == 0) return 0;
+    if (gschur_cuda_device_count() < 1) return fail(GSCHUR_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (flags & GSCHUR_FLAG_DEVICE_PTRS) {
+        rc = enqueue_device(kind, MODE_SCHUR, n, batch, A, lda, strideA, Z, ldz, strideZ, w, nullptr, scale, maxiter,
+                            info, stats, (cudaStream_t)0, flags);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
+        if (!info) return 0;
+        std::vector<int32_t> h((size_t)batch);
+        CUDA_TRY(cudaMemcpy(h.data(), info, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost));
+        int64_t bad = 0;
+        for (int64_t b = 0; b < batch; ++b) {
+            if (h[b] == GSCHUR_ERR_SUBDIAG) return fail(GSCHUR_ERR_SUBDIAG, "ArgumentError: algorithm assumes real subdiagonal");
+            if (h[b] > 0) ++bad;
+        }
+        return (int)bad;
+    }
+    HostJob J;
+    J.kind = kind;
+    J.mode = MODE_SCHUR;
+    J.n = n;
+    J.lda = lda;
+    J.ldz = ldz;
+    J.scale = scale;
+    J.maxiter = maxiter;
+    J.strideA = strideA;
+    J.strideZ = strideZ;
+    J.A = (char*)A;
+    J.Z = (char*)Z;
+    J.w = (char*)w;
+    J.tau = nullptr;
+    J.info = info;
+    J.stats = stats;
+    J.flags = flags;
+    return run_host(J, batch, devices, ndev);
+}
+
+int gschur_cuda_hessenberg_batched(int kind, int n, int64_t batch, void* A, int lda, int64_t strideA, void* tau,
+                                   void* Q, int ldq, int64_t strideQ, const int* devices, int ndev, uint32_t flags) {
+    g_err.clear();
+    int dummy = 0;
+    int rc = check_args(kind, n, batch, A, lda, strideA, Q, ldq, strideQ, &dummy);
+    if (rc) return rc;
+    if (n == 0 || batch == 0) return 0;
+    if (n > 1 && !tau) return fail(GSCHUR_ERR_ARG, "tau is NULL");
+    if (gschur_cuda_device_count() < 1) return fail(GSCHUR_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (flags & GSCHUR_FLAG_DEVICE_PTRS) {
+        rc = enqueue_device(kind, MODE_HESSENBERG, n, batch, A, lda, strideA, Q, ldq, strideQ, nullptr, tau, 0, 0,
+                            nullptr, nullptr, (cudaStream_t)0, 0);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
+        return 0;
+    }
+    HostJob J;
+    J.kind = kind;
+    J.mode = MODE_HESSENBERG;
+    J.n = n;
+    J.lda = lda;
+    J.ldz = ldq;
+    J.scale = 0;
+    J.maxiter = 0;
+    J.strideA = strideA;
+    J.strideZ = strideQ;
+    J.A = (char*)A;
+    J.Z = (char*)Q;
+    J.w = nullptr;
+    J.tau = (char*)tau;
+    J.info = nullptr;
+    J.stats = nullptr;
+    J.flags = 0;
+    return run_host(J, batch, devices, ndev);
+}
+
+}  // extern "C"

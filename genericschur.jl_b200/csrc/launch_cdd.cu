@@ -1,0 +1,7 @@
+// Kernel instantiations for element kind cdd (one translation unit per kind keeps builds parallel).
+#include "batched.cuh"
+namespace gs {
+int launch_cdd(const BatchedParams& p, int dev_sms, cudaStream_t stream, std::string* err) {
+    return launch_t<cx<dd_t>>(p, dev_sms, stream, err);
+}
+}  // namespace gs

@@ -1,0 +1,272 @@
+// Device scalar types of the Schur kernels: Float64, an in-kernel double-double ("Float64x2"), and
+// Complex of either.  Arithmetic conventions follow what the reference's generic Julia code gets from
+// its element types (src/GenericSchur.jl is generic over T<:AbstractFloat / Complex{T}): 4-multiply
+// complex product, scaled complex division, hypot-based modulus.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace gs {
+
+#define GS_DEV __device__ __forceinline__
+
+// ------------------------------------------------------------------------------------------------
+// double-double.  Error-free transformations with explicit round-to-nearest intrinsics so that the
+// compiler can neither contract nor reassociate them.
+// ------------------------------------------------------------------------------------------------
+struct __align__(16) dd_t {
+    double hi, lo;
+};
+
+GS_DEV dd_t mk_dd(double h, double l = 0.0) {
+    dd_t r;
+    r.hi = h;
+    r.lo = l;
+    return r;
+}
+GS_DEV void two_sum(double a, double b, double& s, double& e) {
+    s = __dadd_rn(a, b);
+    double bb = __dsub_rn(s, a);
+    e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+}
+GS_DEV void quick_two_sum(double a, double b, double& s, double& e) {
+    s = __dadd_rn(a, b);
+    e = __dsub_rn(b, __dsub_rn(s, a));
+}
+GS_DEV void two_prod(double a, double b, double& p, double& e) {
+    p = __dmul_rn(a, b);
+    e = __fma_rn(a, b, -p);
+}
+// IEEE-style (accurate) addition: 20 flops
+GS_DEV dd_t operator+(const dd_t& a, const dd_t& b) {
+    double s1, s2, t1, t2;
+    two_sum(a.hi, b.hi, s1, s2);
+    two_sum(a.lo, b.lo, t1, t2);
+    s2 = __dadd_rn(s2, t1);
+    quick_two_sum(s1, s2, s1, s2);
+    s2 = __dadd_rn(s2, t2);
+    quick_two_sum(s1, s2, s1, s2);
+    // inf/nan in the leading sum would otherwise poison lo with nan and hide an honest inf
+    if (!isfinite(s1)) s2 = 0.0;
+    return mk_dd(s1, s2);
+}
+GS_DEV dd_t operator-(const dd_t& a) { return mk_dd(-a.hi, -a.lo); }
+GS_DEV dd_t operator-(const dd_t& a, const dd_t& b) { return a + (-b); }
+GS_DEV dd_t operator*(const dd_t& a, const dd_t& b) {
+    double p1, p2;
+    two_prod(a.hi, b.hi, p1, p2);
+    p2 = __fma_rn(a.hi, b.lo, p2);
+    p2 = __fma_rn(a.lo, b.hi, p2);
+    quick_two_sum(p1, p2, p1, p2);
+    if (!isfinite(p1) || p1 == 0.0) p2 = 0.0;
+    return mk_dd(p1, p2);
+}
+GS_DEV dd_t dd_mul_d(const dd_t& a, double b) {
+    double p1, p2;
+    two_prod(a.hi, b, p1, p2);
+    p2 = __fma_rn(a.lo, b, p2);
+    quick_two_sum(p1, p2, p1, p2);
+    if (!isfinite(p1) || p1 == 0.0) p2 = 0.0;
+    return mk_dd(p1, p2);
+}
+GS_DEV dd_t operator/(const dd_t& a, const dd_t& b) {
+    double q1 = __ddiv_rn(a.hi, b.hi);
+    if (!isfinite(q1) || q1 == 0.0) return mk_dd(q1, 0.0);
+    dd_t r = a - dd_mul_d(b, q1);
+    double q2 = __ddiv_rn(r.hi, b.hi);
+    r = r - dd_mul_d(b, q2);
+    double q3 = __ddiv_rn(r.hi, b.hi);
+    double s, e;
+    quick_two_sum(q1, q2, s, e);
+    return mk_dd(s, e) + mk_dd(q3);
+}
+GS_DEV bool operator==(const dd_t& a, const dd_t& b) { return a.hi == b.hi && a.lo == b.lo; }
+GS_DEV bool operator!=(const dd_t& a, const dd_t& b) { return !(a == b); }
+GS_DEV bool operator<(const dd_t& a, const dd_t& b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+GS_DEV bool operator>(const dd_t& a, const dd_t& b) { return b < a; }
+GS_DEV bool operator<=(const dd_t& a, const dd_t& b) { return a.hi < b.hi || (a.hi == b.hi && a.lo <= b.lo); }
+GS_DEV bool operator>=(const dd_t& a, const dd_t& b) { return b <= a; }
+GS_DEV dd_t& operator+=(dd_t& a, const dd_t& b) { a = a + b; return a; }
+GS_DEV dd_t& operator-=(dd_t& a, const dd_t& b) { a = a - b; return a; }
+GS_DEV dd_t& operator*=(dd_t& a, const dd_t& b) { a = a * b; return a; }
+GS_DEV dd_t& operator/=(dd_t& a, const dd_t& b) { a = a / b; return a; }
+
+GS_DEV dd_t dd_sqrt(const dd_t& a) {
+    if (!(a.hi > 0.0)) return (a.hi == 0.0) ? mk_dd(0.0) : mk_dd(nan(""));
+    if (!isfinite(a.hi)) return a;
+    // Karp: x ~ 1/sqrt(a);  sqrt(a) ~ a x + (a - (a x)^2) x / 2
+    double x = __drcp_rn(__dsqrt_rn(a.hi));
+    double ax = __dmul_rn(a.hi, x);
+    dd_t axd = mk_dd(ax);
+    dd_t r = a - axd * axd;
+    double corr = __dmul_rn(r.hi, __dmul_rn(x, 0.5));
+    double s, e;
+    two_sum(ax, corr, s, e);
+    return mk_dd(s, e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// real-scalar traits and the handful of real functions the algorithm uses
+// ------------------------------------------------------------------------------------------------
+template <class R> struct rtraits;
+template <> struct rtraits<double> {
+    GS_DEV static double eps() { return 2.220446049250313e-16; }
+    GS_DEV static double floatmin() { return 2.2250738585072014e-308; }
+    GS_DEV static double floatmax() { return 1.7976931348623157e308; }
+    GS_DEV static double from(double x) { return x; }
+    static constexpr int ndoubles = 1;
+};
+template <> struct rtraits<dd_t> {
+    // eps = 2^-104, floatmin = 2^-969 (low limb stays a normal Float64), floatmax = floatmax(Float64)
+    GS_DEV static dd_t eps() { return mk_dd(4.930380657631324e-32); }
+    GS_DEV static dd_t floatmin() { return mk_dd(2.004168360008973e-292); }
+    GS_DEV static dd_t floatmax() { return mk_dd(1.7976931348623157e308); }
+    GS_DEV static dd_t from(double x) { return mk_dd(x); }
+    static constexpr int ndoubles = 2;
+};
+
+GS_DEV double r_abs(double x) { return fabs(x); }
+GS_DEV dd_t r_abs(const dd_t& x) { return (x.hi < 0.0 || (x.hi == 0.0 && x.lo < 0.0)) ? -x : x; }
+GS_DEV double r_sqrt(double x) { return __dsqrt_rn(x); }
+GS_DEV dd_t r_sqrt(const dd_t& x) { return dd_sqrt(x); }
+GS_DEV bool r_signbit(double x) { return signbit(x); }
+GS_DEV bool r_signbit(const dd_t& x) { return signbit(x.hi); }
+GS_DEV double r_hi(double x) { return x; }
+GS_DEV double r_hi(const dd_t& x) { return x.hi; }
+GS_DEV bool r_isnan(double x) { return isnan(x); }
+GS_DEV bool r_isnan(const dd_t& x) { return isnan(x.hi) || isnan(x.lo); }
+template <class R> GS_DEV R r_max(const R& a, const R& b) { return (a < b) ? b : a; }
+template <class R> GS_DEV R r_min(const R& a, const R& b) { return (b < a) ? b : a; }
+template <class R> GS_DEV R r_copysign(const R& m, const R& s) {
+    R a = r_abs(m);
+    return r_signbit(s) ? -a : a;
+}
+template <class R> GS_DEV R r_const(double x) { return rtraits<R>::from(x); }
+// safemin, src/util.jl:5-12 : for both types 1/floatmax < floatmin so safemin == floatmin
+template <class R> GS_DEV R r_safemin() { return rtraits<R>::floatmin(); }
+
+// sqrt(a^2 + b^2 + c^2 + d^2) without intermediate over/underflow (dlapy3-style, src/util.jl:562-570)
+template <class R> GS_DEV R r_hypot4(const R& a, const R& b, const R& c, const R& d) {
+    R aa = r_abs(a), ab = r_abs(b), ac = r_abs(c), ad = r_abs(d);
+    R w = r_max(r_max(aa, ab), r_max(ac, ad));
+    if (w == r_const<R>(0.0) || r_isnan(w)) return w + aa + ab + ac + ad;   // 0, or propagate nan
+    R rw = r_const<R>(1.0) / w;
+    R x = aa * rw, y = ab * rw, z = ac * rw, t = ad * rw;
+    return w * r_sqrt(x * x + y * y + z * z + t * t);
+}
+template <class R> GS_DEV R r_hypot(const R& a, const R& b) {
+    return r_hypot4(a, b, r_const<R>(0.0), r_const<R>(0.0));
+}
+
+// ------------------------------------------------------------------------------------------------
+// complex
+// ------------------------------------------------------------------------------------------------
+template <class R> struct __align__(16) cx {
+    R re, im;
+};
+template <class R> GS_DEV cx<R> mk_cx(const R& re, const R& im) {
+    cx<R> r;
+    r.re = re;
+    r.im = im;
+    return r;
+}
+template <class R> GS_DEV cx<R> operator+(const cx<R>& a, const cx<R>& b) { return mk_cx<R>(a.re + b.re, a.im + b.im); }
+template <class R> GS_DEV cx<R> operator-(const cx<R>& a, const cx<R>& b) { return mk_cx<R>(a.re - b.re, a.im - b.im); }
+template <class R> GS_DEV cx<R> operator-(const cx<R>& a) { return mk_cx<R>(-a.re, -a.im); }
+template <class R> GS_DEV cx<R> operator*(const cx<R>& a, const cx<R>& b) {
+    return mk_cx<R>(a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re);
+}
+template <class R> GS_DEV cx<R> operator*(const cx<R>& a, const R& b) { return mk_cx<R>(a.re * b, a.im * b); }
+template <class R> GS_DEV cx<R> operator*(const R& a, const cx<R>& b) { return mk_cx<R>(a * b.re, a * b.im); }
+template <class R> GS_DEV cx<R> operator/(const cx<R>& a, const R& b) { return mk_cx<R>(a.re / b, a.im / b); }
+template <class R> GS_DEV cx<R> operator/(const cx<R>& a, const cx<R>& b) {   // Smith
+    if (r_abs(b.re) >= r_abs(b.im)) {
+        R r = b.im / b.re;
+        R den = b.re + r * b.im;
+        return mk_cx<R>((a.re + a.im * r) / den, (a.im - a.re * r) / den);
+    } else {
+        R r = b.re / b.im;
+        R den = b.im + r * b.re;
+        return mk_cx<R>((a.re * r + a.im) / den, (a.im * r - a.re) / den);
+    }
+}
+template <class R> GS_DEV cx<R>& operator+=(cx<R>& a, const cx<R>& b) { a = a + b; return a; }
+template <class R> GS_DEV cx<R>& operator-=(cx<R>& a, const cx<R>& b) { a = a - b; return a; }
+template <class R> GS_DEV cx<R>& operator*=(cx<R>& a, const cx<R>& b) { a = a * b; return a; }
+template <class R> GS_DEV cx<R>& operator*=(cx<R>& a, const R& b) { a = a * b; return a; }
+template <class R> GS_DEV cx<R> cconj(const cx<R>& a) { return mk_cx<R>(a.re, -a.im); }
+GS_DEV double cconj(double a) { return a; }
+GS_DEV dd_t cconj(const dd_t& a) { return a; }
+template <class R> GS_DEV R c_abs(const cx<R>& a) { return r_hypot(a.re, a.im); }
+template <class R> GS_DEV R abs1(const cx<R>& a) { return r_abs(a.re) + r_abs(a.im); }   // src/util.jl:31-32
+GS_DEV double abs1(double a) { return fabs(a); }
+GS_DEV dd_t abs1(const dd_t& a) { return r_abs(a); }
+// principal square root: rho = sqrt((|z| + |x|)/2), eta = y / (2 rho), on a copy scaled by max(|x|,|y|)
+template <class R> GS_DEV cx<R> c_sqrt(const cx<R>& z) {
+    R zero = r_const<R>(0.0), half = r_const<R>(0.5);
+    if (z.re == zero && z.im == zero) return mk_cx<R>(zero, z.im);
+    R m = r_max(r_abs(z.re), r_abs(z.im));
+    R x = z.re / m, y = z.im / m;
+    R rho = r_sqrt((r_hypot(x, y) + r_abs(x)) * half);
+    R sm = r_sqrt(m);
+    R xi = rho, eta = (y / rho) * half;
+    if (x < zero) {
+        xi = r_abs(eta);
+        eta = r_copysign(rho, y);
+    }
+    return mk_cx<R>(xi * sm, eta * sm);
+}
+
+// element-type traits
+template <class T> struct etraits;
+template <> struct etraits<double> {
+    typedef double real;
+    static constexpr bool is_complex = false;
+};
+template <> struct etraits<dd_t> {
+    typedef dd_t real;
+    static constexpr bool is_complex = false;
+};
+template <class R> struct etraits<cx<R>> {
+    typedef R real;
+    static constexpr bool is_complex = true;
+};
+template <class T> GS_DEV T e_zero();
+template <> GS_DEV double e_zero<double>() { return 0.0; }
+template <> GS_DEV dd_t e_zero<dd_t>() { return mk_dd(0.0); }
+template <> GS_DEV cx<double> e_zero<cx<double>>() { return mk_cx<double>(0.0, 0.0); }
+template <> GS_DEV cx<dd_t> e_zero<cx<dd_t>>() { return mk_cx<dd_t>(mk_dd(0.0), mk_dd(0.0)); }
+template <class T> GS_DEV T e_one();
+template <> GS_DEV double e_one<double>() { return 1.0; }
+template <> GS_DEV dd_t e_one<dd_t>() { return mk_dd(1.0); }
+template <> GS_DEV cx<double> e_one<cx<double>>() { return mk_cx<double>(1.0, 0.0); }
+template <> GS_DEV cx<dd_t> e_one<cx<dd_t>>() { return mk_cx<dd_t>(mk_dd(1.0), mk_dd(0.0)); }
+
+// modulus of an element (norm(A, Inf) of a Matrix is max |a_ij|, src/util.jl:17)
+GS_DEV double e_abs(double a) { return fabs(a); }
+GS_DEV dd_t e_abs(const dd_t& a) { return r_abs(a); }
+template <class R> GS_DEV R e_abs(const cx<R>& a) { return c_abs(a); }
+// max over |re|, |im| parts (used by the scaled 2-norm)
+GS_DEV double e_maxpart(double a) { return fabs(a); }
+GS_DEV dd_t e_maxpart(const dd_t& a) { return r_abs(a); }
+template <class R> GS_DEV R e_maxpart(const cx<R>& a) { return r_max(r_abs(a.re), r_abs(a.im)); }
+// |a*s|^2 summed over parts
+GS_DEV double e_sq_scaled(double a, double s) { double t = a * s; return t * t; }
+GS_DEV dd_t e_sq_scaled(const dd_t& a, const dd_t& s) { dd_t t = a * s; return t * t; }
+template <class R> GS_DEV R e_sq_scaled(const cx<R>& a, const R& s) {
+    R x = a.re * s, y = a.im * s;
+    return x * x + y * y;
+}
+// element * real
+GS_DEV double e_scale(double a, double s) { return a * s; }
+GS_DEV dd_t e_scale(const dd_t& a, const dd_t& s) { return a * s; }
+template <class R> GS_DEV cx<R> e_scale(const cx<R>& a, const R& s) { return mk_cx<R>(a.re * s, a.im * s); }
+
+// warp shuffles for every scalar type
+GS_DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+GS_DEV dd_t shfl_xor(const dd_t& v, int m) {
+    return mk_dd(__shfl_xor_sync(0xffffffffu, v.hi, m), __shfl_xor_sync(0xffffffffu, v.lo, m));
+}
+
+}  // namespace gs

@@ -1,0 +1,114 @@
+/*
+ * libgschur_cuda — C ABI of the B200 (sm_100a) Schur hot path.
+ *
+ * Drop-in boundary for RalphAS/GenericSchur.jl's `gschur!` / `schur!` / `eigvals!` / `hessenberg!`:
+ * the reference has no FFI seam (it is pure Julia), so these entry points are what a Julia `ccall`
+ * shim binds in place of the Julia methods cited at each declaration (paths relative to the reference
+ * tree).  INTEGRATION.md shows the shim.  Plain pointers and sizes only; no torch / CUDA types.
+ *
+ * Element kinds (column-major matrices, Julia `Matrix` layout):
+ *   GSCHUR_F64  Float64                      8 B / element
+ *   GSCHUR_C64  ComplexF64 (re, im)         16 B
+ *   GSCHUR_DD   double-double (hi, lo)      16 B   (DoubleFloats.Double64 / MultiFloats.Float64x2 layout)
+ *   GSCHUR_CDD  Complex{double-double} (re.hi, re.lo, im.hi, im.lo)  32 B
+ * Eigenvalues `w` are always complex: 2 doubles per value for F64/C64, 4 doubles for DD/CDD.
+ *
+ * Return convention: 0 = success; > 0 = number of matrices that did not converge (their info[] > 0; the
+ * shim throws UnconvergedException("iteration limit $maxiter reached"), src/GenericSchur.jl:235,555);
+ * < 0 = argument or CUDA error (gschur_cuda_last_error() has the text; the shim throws
+ * DimensionMismatch / ArgumentError / ErrorException).
+ *
+ * There is no CPU fallback: every entry point fails with GSCHUR_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef GSCHUR_CUDA_H
+#define GSCHUR_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSCHUR_F64 0
+#define GSCHUR_C64 1
+#define GSCHUR_DD 2
+#define GSCHUR_CDD 3
+
+/* flags */
+#define GSCHUR_FLAG_DEVICE_PTRS 0x1u /* A, Z, w, info, stats are device pointers on the current device      */
+#define GSCHUR_FLAG_HESS_INPUT 0x2u  /* A already upper Hessenberg: skip the reduction (gschur!(H::Hessenberg, Z)) */
+#define GSCHUR_FLAG_CHECK_SUBDIAG 0x4u /* with HESS_INPUT, complex kinds: reject a non-real sub-diagonal (checksd) */
+
+/* error codes (negative returns) */
+#define GSCHUR_ERR_ARG (-1)      /* bad kind / n / leading dimension / stride / NULL pointer */
+#define GSCHUR_ERR_CUDA (-2)     /* CUDA runtime failure or no usable device */
+#define GSCHUR_ERR_SIZE (-3)     /* n not supported by any kernel for this kind */
+#define GSCHUR_ERR_SUBDIAG (-4)  /* "algorithm assumes real subdiagonal" (src/GenericSchur.jl:206-210) */
+
+#define GSCHUR_STATS_PER_MATRIX 4 /* sweeps, reflector applications, exceptional shifts, iterations */
+
+int gschur_cuda_version(void);
+int gschur_cuda_device_count(void);
+/* thread-local text of the last error on this thread ("" if none) */
+const char* gschur_cuda_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t gschur_cuda_launch_count(void);
+/* largest n the batched (one matrix per CTA / cluster) kernels take for `kind`; 0 if kind is invalid */
+int gschur_cuda_max_batched_n(int kind);
+
+/*
+ * Batched Schur decomposition: for b in [0, batch): A_b = Z_b T_b Z_b^H.
+ * Replaces gschur!(A::StridedMatrix{Complex{T}}; wantZ, scale)  src/GenericSchur.jl:350-372
+ *      and gschur!(A::StridedMatrix{T<:AbstractFloat}; wantZ, scale) src/GenericSchur.jl:805-835
+ * (and through them schur! src/pirates.jl:8-10 and eigvals! src/pirates.jl:17-27), one call per batch.
+ *
+ *   A      in: A_b (destroyed).  out: T_b — upper triangular (complex kinds) or quasi-upper-triangular in
+ *          standard form (real kinds); entries below are written as exact zeros.
+ *   lda, strideA   leading dimension (>= n) and distance between consecutive matrices, in elements.
+ *   Z      out: Schur vectors, or NULL for wantZ = false (the eigvals! path).
+ *   w      out: n*batch complex eigenvalues, w[b*n + j] pairs with T_b[j,j].
+ *   scale  non-zero: apply _scale! (src/util.jl:14-29) before and undo it after, as the reference does.
+ *   maxiter <= 0 selects the reference default 100*n.
+ *   info   per matrix (NULL ok): 0 converged; k > 0: iteration limit hit with the active block ending at row k.
+ *   stats  NULL or GSCHUR_STATS_PER_MATRIX uint32 per matrix.
+ *   devices/ndev  host-pointer mode only: the batch is split in contiguous slices over these CUDA devices
+ *          (NULL / 0 = device 0).  Ignored with GSCHUR_FLAG_DEVICE_PTRS.
+ */
+int gschur_cuda_batched(int kind, int n, int64_t batch,
+                        void* A, int lda, int64_t strideA,
+                        void* Z, int ldz, int64_t strideZ,
+                        void* w, int scale, int maxiter,
+                        int32_t* info, uint32_t* stats,
+                        const int* devices, int ndev, uint32_t flags);
+
+/*
+ * Same, device-resident and asynchronous: all pointers are device pointers on the current device, the work is
+ * enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream) and the call returns
+ * without synchronising.  Return value is 0 or a negative error; convergence is reported through info[] only.
+ */
+int gschur_cuda_batched_async(int kind, int n, int64_t batch,
+                              void* A, int lda, int64_t strideA,
+                              void* Z, int ldz, int64_t strideZ,
+                              void* w, int scale, int maxiter,
+                              int32_t* info, uint32_t* stats,
+                              void* stream, uint32_t flags);
+
+/*
+ * Batched Householder reduction to Hessenberg form, A_b = Q_b H_b Q_b^H.
+ * Replaces _hessenberg!(A) src/hessenberg.jl:3-17 (LinearAlgebra.hessenberg! src/pirates.jl:232) and
+ * _materializeQ(H) src/hessenberg.jl:150-166.
+ *   A    in: A_b; out: the factors exactly as the reference leaves them — H on and above the sub-diagonal,
+ *        reflector tails below it (complex kinds: the sub-diagonal is real).
+ *   tau  out: (n-1)*batch reflector scalars (element type of `kind`), stride n-1.
+ *   Q    out: explicit Q_b, or NULL.
+ */
+int gschur_cuda_hessenberg_batched(int kind, int n, int64_t batch,
+                                   void* A, int lda, int64_t strideA,
+                                   void* tau,
+                                   void* Q, int ldq, int64_t strideQ,
+                                   const int* devices, int ndev, uint32_t flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSCHUR_CUDA_H */
