@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — the Schur hot path's headline benchmark on B200.
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                     (the reference algorithm's CPU implementation, host cores)
+
+Metric (BASELINE.json): batched n=64 Schur matrices/s.  Workload at every N: BASELINE config 3's shape — random
+64x64 ComplexF64 matrices (re, im ~ U[0,1)), 65536 per GPU (weak scaling: the batch is split in independent
+per-GPU shards, no data-path collective).  One "step" = gschur! of one such batch, with Z.
+
+  value  device-resident matrices/s: inputs already in HBM when the timed region starts (CUDA events on the launching
+         stream, W >= 3 warm-ups, the 4 GiB input exceeds L2, max over ranks).
+  e2e    the same metric through the public host API (gschur_ on pinned host arrays): H2D of A, D2H of T, Z, w, info
+         inside the timed region.
+  roofline  FP64-FMA bound: nominal flops per matrix (88 n^3 complex / 25 n^3 real) x batch / kernel
+         time, against the DFMA peak measured live by the library's micro-kernel; HBM view alongside.
+  cpu_baseline  the CPU oracle (C++ restatement of the reference algorithm, kind "port") over a bounded sample with all
+         host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_oracle, load_package  # noqa: E402
+
+WORKLOADS = {
+    # name: (kind, n, per-GPU batch, nominal flops per matrix, description)
+    "cfg3": (1, 64, 65536, 88 * 64 ** 3, "65536 x 64x64 ComplexF64 per GPU (BASELINE config 3 shape), with Z"),
+    "cfg2": (0, 32, 16384, 25 * 32 ** 3, "16384 x 32x32 Float64 per GPU (BASELINE config 2), with Z"),
+    "f64n64": (0, 64, 65536, 25 * 64 ** 3, "65536 x 64x64 Float64 per GPU, with Z"),
+}
+METRIC = "batched n=64 Schur matrices/s"
+UNIT = "matrices/s"
+
+
+def shard_bounds(total, world, rank):
+    """Contiguous slice [lo, hi) of `total` units owned by `rank` (the only multi-GPU 'partitioning' there is)."""
+    return total * rank // world, total * (rank + 1) // world
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md's clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i",
+                 str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(kind, n, batch, seed):
+    rng = np.random.default_rng(seed)
+    if kind == 1:
+        A = np.empty((n, n, batch), dtype=np.complex128, order="F")
+        step = max(1, batch // 16)
+        for lo in range(0, batch, step):
+            hi = min(batch, lo + step)
+            A[:, :, lo:hi] = rng.random((n, n, hi - lo)) + 1j * rng.random((n, n, hi - lo))
+    else:
+        A = np.asfortranarray(rng.random((n, n, batch)))
+    return A
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(kind, n, batch, seed, cores=None, steps=1):
+    """The oracle's batched driver over a bounded sample of the same workload with all host threads."""
+    O = load_oracle()
+    cores = cores or os.cpu_count() or 1
+    per_core = 512 if (kind == 1 and n == 64) else 4096
+    sample = int(min(batch, cores * per_core))
+    A = make_inputs(kind, n, sample, seed)
+    best = None
+    for _ in range(steps):
+        Ac = A.copy(order="F")
+        t0 = time.perf_counter()
+        _, _, _, info = O.gschur_batched(Ac, kind, wantZ=True, scale=True, nthreads=cores)
+        dt = time.perf_counter() - t0
+        assert not info.any()
+        best = dt if best is None else min(best, dt)
+    return {"value": sample / best, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sample} of the {batch} matrices ({n}x{n}, same generator/seed), {cores} host threads, "
+                      f"oracle/ C++ restatement of gschur! (Julia is not installed; see DESIGN.md)"}, sample, best
+
+
+def run_reference(args):
+    kind, n, batch, flops, desc = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_core = 256 if (kind == 1 and n == 64) else 2048
+    sample = int(min(batch, cores * per_core))
+    O = load_oracle()
+    A = make_inputs(kind, n, sample, 1234 + 3)
+    times = []
+    for it in range(args.warmup + args.steps):
+        Ac = A.copy(order="F")
+        t0 = time.perf_counter()
+        _, _, _, info = O.gschur_batched(Ac, kind, wantZ=True, scale=True, nthreads=cores)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    val = sample / (ms * 1e-3)
+    sample_desc = (f"each step = {sample} matrices of the workload ({cores} host threads x {per_core}); "
+                   "oracle/ C++ restatement of the reference's gschur! (the Julia package cannot run here)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload + ": " + desc, "n": n, "element": "ComplexF64" if kind == 1 else "Float64",
+                   "per_gpu_batch": batch, "sample_per_step": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (development only)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    gs = load_package()
+    kind, n, batch, flops_per_matrix, desc = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        # a bare `python bench.py --gpus N` without torchrun runs as one rank
+        world = max(world, 1)
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the Schur path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs: this rank's shard (weak scaling: `batch` matrices per GPU), resident in HBM -------------------
+    seed = 1234 + 3 + 1000 * rank
+    A_host_np = make_inputs(kind, n, batch, seed)
+    tdt = torch.complex128 if kind == 1 else torch.float64
+    esz = 16 if kind == 1 else 8
+    # torch views of the Fortran-ordered numpy data: shape (batch, n, n) C-order == (n, n, batch) F-order in memory
+    A_host = torch.from_numpy(A_host_np.T)            # (batch, n, n) view, contiguous
+    assert A_host.is_contiguous()
+    A0 = A_host.cuda()
+    A = torch.empty_like(A0)
+    Z = torch.empty_like(A0)
+    w = torch.empty((batch, n), dtype=torch.complex128, device="cuda")
+    info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+    stats = torch.zeros((batch, 4), dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        gs.gschur_device_(kind, n, batch, A.data_ptr(), Z.data_ptr(), w.data_ptr(), info.data_ptr(),
+                          stats.data_ptr(), scale=True, stream=stream)
+
+    for _ in range(args.warmup):
+        A.copy_(A0)
+        step()
+    torch.cuda.synchronize()
+    assert int((info != 0).sum().item()) == 0, "warm-up: some matrices did not converge"
+    executed_units = stats[:, 1].to(torch.float64).mean().item()   # reflector applications per matrix (informative)
+
+    sampler = ClockSampler(local_rank)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = gs.launch_count()
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for k in range(args.steps):
+        A.copy_(A0)                      # restore the input (untimed: outside the event pair)
+        evs[k][0].record()
+        step()
+        evs[k][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    launches = gs.launch_count() - launches0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = float(sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * batch / (ms_per_step * 1e-3)
+    assert int((info != 0).sum().item()) == 0
+
+    # ---- end to end through the public host API (pinned host buffers, H2D + D2H inside the timed region) -------
+    e2e = None
+    if args.e2e_steps > 0:
+        Ah = torch.empty((batch, n, n), dtype=tdt).pin_memory()
+        Zh = torch.empty((batch, n, n), dtype=tdt).pin_memory()
+        Ah_np = Ah.numpy().T            # (n, n, batch) Fortran-ordered view of the pinned buffer
+        Zh_np = Zh.numpy().T
+        assert Ah_np.flags.f_contiguous
+        times = []
+        for it in range(1 + args.e2e_steps):
+            Ah.copy_(A_host)
+            barrier()
+            t0 = time.perf_counter()
+            S = gs.gschur_(Ah_np, Z=Zh_np, devices=[local_rank])
+            checksum = float(np.abs(S.values[:, ::4097]).sum())    # touch the result on the host
+            dt = time.perf_counter() - t0
+            if it > 0:
+                times.append(dt)
+        e2e_s = float(np.mean(times))
+        if world > 1:
+            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        h2d = batch * n * n * esz
+        d2h = 2 * batch * n * n * esz + batch * n * 16 + batch * 4 + batch * 16
+        e2e = {"value": world * batch / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps, "api": "genericschur_jl_b200.gschur_ (host arrays)",
+               "checksum": checksum}
+        del Ah, Zh
+
+    if rank == 0:
+        hbm_peak, hbm_src = measured_peaks()
+        fp64_peak, _ = gs.measure_fp64_peak()
+        kernel_ms = float(np.mean(step_ms))            # one launch per step: the step IS the dominant kernel
+        alg_flops = flops_per_matrix * batch
+        alg_bytes = 3 * n * n * esz * batch + n * 16 * batch
+        achieved_tf = alg_flops / (kernel_ms * 1e-3) / 1e12
+        roofline = {
+            "bound": "fp64_fma", "kernel": "gschur_batched_kernel", "achieved": achieved_tf, "peak": fp64_peak,
+            "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": None,
+            "peak_source": "measured live (library DFMA micro-kernel; MEASURED_PEAKS.json has no FP64 figure)",
+            "algorithmic_flops_per_matrix": flops_per_matrix,
+            "executed_reflector_applications_per_matrix": executed_units,
+            "hbm_view": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                         "algorithmic_bytes_per_matrix": alg_bytes // batch},
+        }
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu, _, _ = cpu_baseline(kind, n, batch, 1234 + 3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload + ": " + desc, "n": n,
+                       "element": "ComplexF64" if kind == 1 else "Float64", "per_gpu_batch": batch,
+                       "l2_policy": "inputs_exceed_l2" if batch * n * n * esz > 2 * 126e6 else "inputs_fit_l2",
+                       "sharding": "independent per-GPU shards, no collective"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -112,6 +112,16 @@ def launch_count():
     return int(_lib.lib().gschur_cuda_launch_count())
 
 
+def measure_fp64_peak():
+    """(TFLOP/s, ms) of a DFMA-only micro-kernel on the current device: the FP64 roofline denominator."""
+    t = ctypes.c_double(0.0)
+    ms = ctypes.c_double(0.0)
+    rc = _lib.lib().gschur_cuda_measure_fp64_peak(ctypes.byref(t), ctypes.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"gschur_cuda_measure_fp64_peak failed: {rc}")
+    return t.value, ms.value
+
+
 def max_batched_n(kind):
     return _lib.lib().gschur_cuda_max_batched_n(kind)
 

@@ -26,6 +26,7 @@ EXPORTS = [
     "gschur_cuda_batched",
     "gschur_cuda_batched_async",
     "gschur_cuda_hessenberg_batched",
+    "gschur_cuda_measure_fp64_peak",
 ]
 
 _lib = None
@@ -59,6 +60,8 @@ def lib():
         L.gschur_cuda_batched_async.restype = ci
         L.gschur_cuda_hessenberg_batched.argtypes = [ci, ci, i64, vp, ci, i64, vp, vp, ci, i64, vp, ci, u32]
         L.gschur_cuda_hessenberg_batched.restype = ci
+        L.gschur_cuda_measure_fp64_peak.argtypes = [vp, vp]
+        L.gschur_cuda_measure_fp64_peak.restype = ci
         _lib = L
     return _lib
 

@@ -1,0 +1,60 @@
+// FP64 FMA peak probe: the roofline denominator for the compute-bound batched kernels.  MEASURED_PEAKS.json
+// records HBM and bf16 tensor peaks only, so the FP64 vector peak is measured here, on the same device, by a
+// kernel that does nothing but independent DFMA chains (8 accumulators per thread, fully unrolled).
+#include <cuda_runtime.h>
+#include "../../include/gschur_cuda.h"
+
+namespace {
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1.0, x2 = x0 + 2.0, x3 = x0 + 3.0;
+    double x4 = x0 + 4.0, x5 = x0 + 5.0, x6 = x0 + 6.0, x7 = x0 + 7.0;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            x0 = fma(x0, a, b);
+            x1 = fma(x1, a, b);
+            x2 = fma(x2, a, b);
+            x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b);
+            x5 = fma(x5, a, b);
+            x6 = fma(x6, a, b);
+            x7 = fma(x7, a, b);
+        }
+    }
+    double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[0] = s;   // keeps the chains live without a store in the common case
+}
+}  // namespace
+
+extern "C" int gschur_cuda_measure_fp64_peak(double* tflops, double* ms_out) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return GSCHUR_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return GSCHUR_ERR_CUDA;
+    double* d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return GSCHUR_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) {
+            cudaFree(d);
+            return GSCHUR_ERR_CUDA;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)threads * (double)blocks;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return 0;
+}

@@ -94,6 +94,13 @@ int gschur_cuda_batched_async(int kind, int n, int64_t batch,
                               void* stream, uint32_t flags);
 
 /*
+ * Measures the FP64 FMA peak of the current device with a DFMA-only micro-kernel (the roofline denominator of
+ * the compute-bound batched kernels; MEASURED_PEAKS.json has no FP64 figure).  *tflops receives 2*FMA/s / 1e12,
+ * *ms (NULL ok) the best kernel time.
+ */
+int gschur_cuda_measure_fp64_peak(double* tflops, double* ms);
+
+/*
  * Batched Householder reduction to Hessenberg form, A_b = Q_b H_b Q_b^H.
  * Replaces _hessenberg!(A) src/hessenberg.jl:3-17 (LinearAlgebra.hessenberg! src/pirates.jl:232) and
  * _materializeQ(H) src/hessenberg.jl:150-166.

@@ -1,0 +1,311 @@
+"""GPU parity tests (run on the B200 with -m gpu): the CUDA path, called through the C ABI, against the CPU oracle
+on the same inputs, against the committed golden fixtures, and — at BASELINE.json's full sizes — through
+size-independent properties.
+
+Tolerances (floating point; iteration counts may differ, so nothing here is bit-exact against the oracle):
+  backward error  ||A - Z T Z'||_F / (n ulp ||A||_F) <= tol   and   orthogonality ||Z'Z - I||_F / (n ulp) <= tol,
+  evaluated in MPFR-256, tol = 10 for random inputs and 20 for the LAPACK-style / normal classes — the reference's own
+  thresholds (test/complex.jl:90,127,133,184; test/real.jl:106,130,175), BASELINE.json's acceptance being the 10;
+  eigenvalues: |lambda_gpu - lambda_oracle| <= 1e3 * ulp * ||A||_F / s_i with s_i the reciprocal condition number the
+  reference's eigvalscond would report (src/ordschur.jl:92-106, computed as rconde of src/pirates.jl:109-113);
+  structural post-conditions are exact (`==`), as in the reference's tests.
+"""
+import numpy as np
+import pytest
+
+from common import ULP, csort, fnorm, godunov, match_eigs, reference_classes, structure_ok
+
+pytestmark = pytest.mark.gpu
+
+
+def _eig_tol(O, A):
+    sc = float(np.max(np.abs(A))) or 1.0
+    Ac = np.asfortranarray((A / sc).astype(np.complex128))
+    Tc, _, wc, rc, _ = O.gschur(Ac, 1)
+    assert rc == 0
+    s = O.eigvalscond(Tc, 1)
+    s = np.where(np.isfinite(s) & (s > 0), s, 1e-300)
+    return sc, wc, 1e3 * ULP * fnorm(Ac) / s
+
+
+def _check_one(O, A, T, Z, w, kind, tol, name):
+    ok, why = structure_ok(T, w, kind, tol)
+    assert ok, (name, why)
+    berr, oerr, _ = O.residuals(A, T, Z, kind)
+    assert berr < tol and oerr < tol, (name, berr, oerr)
+    sc, wc, etol = _eig_tol(O, A)
+    d = match_eigs(w / sc, wc, etol)
+    assert np.all(d <= etol), (name, float(np.max(d / etol)))
+
+
+@pytest.mark.parametrize("complex_", [False, True])
+def test_reference_classes(gs, O, complex_):
+    """schurtest (test/complex.jl:1-34, test/real.jl:24-74) over the reference's matrix classes, on the GPU."""
+    kind = gs.C64 if complex_ else gs.F64
+    for name, A, tol in reference_classes(complex_):
+        S = gs.gschur(A)
+        assert S.info == 0, name
+        _check_one(O, A, S.T, S.Z, S.values, kind, tol, name)
+        if name.startswith("normal"):
+            off = fnorm(np.triu(S.T, 1 if complex_ else 2)) / (A.shape[0] * fnorm(A) * ULP)
+            assert off < tol, (name, off)
+
+
+def test_golden_fixtures(gs, O, golden):
+    """GPU eigenvalues against the committed oracle / LAPACK-original eigenvalues (tests/golden/cases.npz)."""
+    for key in golden["names"]:
+        key = str(key)
+        A = np.asfortranarray(golden[key + "__A"])
+        kind, tol = int(golden[key + "__meta"][0]), golden[key + "__meta"][1]
+        S = gs.gschur(A)
+        assert S.info == 0, key
+        berr, oerr, _ = O.residuals(A, S.T, S.Z, kind)
+        assert berr < tol and oerr < tol, (key, berr, oerr)
+        sc, wc, etol = _eig_tol(O, A)
+        for ref in (golden[key + "__w"], golden[key + "__wlapack"]):
+            if np.any(np.isnan(ref)):
+                continue
+            d = match_eigs(S.values / sc, ref / sc, etol)
+            assert np.all(d <= 2 * etol), (key, float(np.max(d / etol)))
+
+
+@pytest.mark.parametrize("kind,n,batch", [(0, 1, 3), (0, 2, 5), (0, 3, 4), (0, 5, 7), (0, 31, 9), (0, 33, 6), (0, 64, 5),
+                                          (0, 65, 3), (0, 100, 2), (1, 1, 3), (1, 2, 5), (1, 3, 4), (1, 17, 6),
+                                          (1, 33, 4), (1, 64, 4), (1, 80, 2)])
+def test_ragged_sizes(gs, O, kind, n, batch):
+    rng = np.random.default_rng(100 * kind + n)
+    A = rng.random((n, n, batch)) + (1j * rng.random((n, n, batch)) if kind else 0)
+    A = np.asfortranarray(A)
+    S = gs.gschur(A)
+    assert not np.any(S.info)
+    for b in range(batch):
+        _check_one(O, A[:, :, b], S.T[:, :, b], S.Z[:, :, b], S.values[:, b], kind, 10, f"n{n}b{b}")
+
+
+def test_empty_inputs(gs):
+    S = gs.gschur(np.zeros((0, 0), order="F"))
+    assert S.T.shape == (0, 0) and S.values.shape == (0,)
+    S = gs.gschur(np.zeros((4, 4, 0), order="F"))
+    assert S.values.shape == (4, 0)
+
+
+def test_wantz_false_same_T(gs):
+    """eigvals! path (src/pirates.jl:17-27): Z does not feed back into H, so T and values are bit-identical."""
+    rng = np.random.default_rng(8)
+    for kind in (0, 1):
+        A = np.asfortranarray(rng.random((32, 32, 8)) + (1j * rng.random((32, 32, 8)) if kind else 0))
+        S1 = gs.gschur(A)
+        S2 = gs.gschur(A, wantZ=False)
+        assert S2.Z.shape == (0, 0)
+        assert np.array_equal(S1.T, S2.T) and np.array_equal(S1.values, S2.values)
+        ev = gs.eigvals(A)
+        for b in range(8):
+            assert np.array_equal(ev[:, b], csort(S1.values[:, b]))
+
+
+def test_strided_and_split_invariance(gs):
+    """lda > n / strided batches, and batch-split invariance: the same matrices give bit-identical results however
+    the batch is split over devices (here: two slices on the same device)."""
+    import ctypes
+    from genericschur_jl_b200 import _lib
+    rng = np.random.default_rng(21)
+    n, batch, lda = 24, 37, 29
+    A = np.asfortranarray(rng.random((n, n, batch)))
+    S = gs.gschur(A)
+    S2 = gs.gschur(A, devices=[0, 0])
+    assert np.array_equal(S.T, S2.T) and np.array_equal(S.Z, S2.Z) and np.array_equal(S.values, S2.values)
+    big = np.zeros((lda, n + 2, batch), order="F")
+    big[:n, :n, :] = A
+    Z = np.zeros_like(big)
+    w = np.zeros((n, batch), dtype=np.complex128, order="F")
+    info = np.zeros(batch, dtype=np.int32)
+    rc = _lib.lib().gschur_cuda_batched(0, n, batch, big.ctypes.data_as(ctypes.c_void_p), lda, lda * (n + 2),
+                                        Z.ctypes.data_as(ctypes.c_void_p), lda, lda * (n + 2),
+                                        w.ctypes.data_as(ctypes.c_void_p), 1, 0, info.ctypes.data_as(ctypes.c_void_p),
+                                        None, None, 0, 0)
+    assert rc == 0
+    assert np.array_equal(big[:n, :n, :], S.T) and np.array_equal(Z[:n, :n, :], S.Z) and np.array_equal(w, S.values)
+    assert np.all(big[n:, :, :] == 0) and np.all(big[:, n:, :] == 0)
+
+
+def test_hessenberg(gs, O):
+    """hesstest (test/complex.jl:36-61, test/real.jl:76-99) incl. the tiny / huge scalings; sub-diagonal real."""
+    rng = np.random.default_rng(1234)
+    for kind in (0, 1):
+        scales = (1.0, 100 * np.finfo(float).tiny) + ((np.finfo(float).max / 100,) if kind == 0 else ())
+        for sc in scales:
+            A = rng.random((32, 32, 4)) + (1j * rng.random((32, 32, 4)) if kind else 0)
+            A = np.asfortranarray(A * sc)
+            Hs = gs.hessenberg(A)
+            for b in range(4):
+                F = Hs.factors[:, :, b]
+                Hm = np.triu(F, -1)
+                berr, oerr, _ = O.residuals(A[:, :, b], Hm, Hs.Q[:, :, b], kind)
+                assert berr < 10 and oerr < 10, (kind, sc, berr, oerr)
+                assert np.all(np.imag(np.diag(Hm, -1)) == 0)
+                Fo, tauo, Qo = O.hessenberg(A[:, :, b], kind)
+                np.testing.assert_allclose(np.triu(F, -1), np.triu(Fo, -1), rtol=0, atol=1e-11 * np.abs(A).max())
+                np.testing.assert_allclose(np.tril(F, -2), np.tril(Fo, -2), rtol=0, atol=1e-11)
+                np.testing.assert_allclose(Hs.tau[:, b], tauo, rtol=0, atol=1e-12)
+
+
+def test_hessenberg_input_entry(gs, O):
+    """gschur!(H::Hessenberg, Z) (src/GenericSchur.jl:194-210, 513-525) and its error behaviour (test/errors.jl:1-10)."""
+    rng = np.random.default_rng(5)
+    n = 20
+    for kind in (0, 1):
+        A = rng.random((n, n)) + (1j * rng.random((n, n)) if kind else 0)
+        H = np.asfortranarray(np.triu(A, -1))
+        if kind:
+            H[np.arange(1, n), np.arange(n - 1)] = np.real(H[np.arange(1, n), np.arange(n - 1)])
+        H0 = H.copy(order="F")
+        Z = np.asfortranarray(np.eye(n, dtype=H.dtype))
+        S = gs.gschur_hess_(H, Z)
+        _check_one(O, H0, S.T, S.Z, S.values, kind, 10, "hess-input")
+    # complex sub-diagonal -> ArgumentError
+    n = 5
+    A = np.asfortranarray(np.diag(np.full(n - 1, -1.0 + 1.0j), -1) + np.triu(rng.random((n, n))))
+    with pytest.raises(gs.ArgumentError):
+        gs.gschur_hess_(A)
+    # Z of the wrong size -> DimensionMismatch
+    with pytest.raises(gs.DimensionMismatch):
+        gs.gschur_hess_(np.asfortranarray(np.triu(rng.random((n, n)), -1)), np.asfortranarray(rng.random((n - 1, n - 1))))
+
+
+def test_unconverged(gs):
+    """NaN input never deflates: the iteration cap (100 n) trips and the host raises UnconvergedException
+    (src/GenericSchur.jl:234-236, 553-556); with check=False the per-matrix info carries the failing block."""
+    rng = np.random.default_rng(1)
+    for kind in (0, 1):
+        A = np.asfortranarray(rng.random((6, 6, 3)) + (1j * rng.random((6, 6, 3)) if kind else 0))
+        A[2, 3, 1] = np.nan
+        with pytest.raises(gs.UnconvergedException):
+            gs.gschur(A)
+        S = gs.gschur(A, check=False)
+        assert S.info[0] == 0 and S.info[2] == 0 and S.info[1] > 0
+        # tiny iteration budget on a healthy matrix
+        S = gs.gschur(np.asfortranarray(A[:, :, 0]), maxiter=2, check=False)
+        assert S.info > 0
+
+
+def test_scaling_classes(gs, O):
+    """_scale! round trip (src/util.jl:14-29; src/GenericSchur.jl:367-370, 830-833) at extreme magnitudes."""
+    rng = np.random.default_rng(2)
+    for mag in (1e-292, 1e-200, 1e250, 8e291):
+        for kind in (0, 1):
+            A = np.asfortranarray((rng.random((12, 12)) + (1j * rng.random((12, 12)) if kind else 0)) * mag)
+            S = gs.gschur(A)
+            _check_one(O, A, S.T, S.Z, S.values, kind, 10, f"mag{mag}")
+
+
+def test_double_double_vs_bigfloat(gs, O):
+    """Double-double kernels against the MPFR-256 oracle (BigFloat(256) stand-in): residual ratios with the dd ulp
+    (2^-104) <= 10, eigenvalues within 1e3 ulp_dd ||A|| / s_i of the 256-bit ones."""
+    rng = np.random.default_rng(77)
+    for kind, n, batch in ((gs.DD, 24, 4), (gs.CDD, 24, 4), (gs.CDD, 48, 2)):
+        lead = 2 if kind == gs.DD else 4
+        A = np.zeros((lead, n, n, batch), order="F")
+        for part in range(0, lead, 2):
+            hi = rng.random((n, n, batch))
+            lo = (rng.random((n, n, batch)) - 0.5) * 2.0 ** -53 * hi
+            s = hi + lo
+            A[part] = s
+            A[part + 1] = lo - (s - hi)
+        A = A.view(gs.DDArray if kind == gs.DD else gs.CDDArray)
+        S = gs.gschur(A)
+        assert not np.any(S.info)
+        for b in range(batch):
+            Ab = np.asfortranarray(np.asarray(A[..., b]))
+            berr, oerr, anorm = O.residuals(Ab, np.asarray(S.T[..., b]), np.asarray(S.Z[..., b]), kind)
+            assert berr < 10 and oerr < 10, (kind, n, b, berr, oerr)
+            Tm, Zm, wm, rc = O.gschur_mp(Ab, kind)
+            assert rc == 0
+            # condition numbers from a complex dd Schur form (oracle)
+            if kind == gs.CDD:
+                Tc = np.asfortranarray(np.asarray(S.T[..., b]))
+            else:
+                Ac = np.zeros((4, n, n), order="F")
+                Ac[0], Ac[1] = Ab[0], Ab[1]
+                Tc, _, _, rc, _ = O.gschur(Ac, 3)
+                assert rc == 0
+            w = np.asarray(S.values[..., b])
+            s = O.eigvalscond(Tc, 3)
+            wg = (w[0] + 1j * w[2])
+            wr = (wm[0] + 1j * wm[2])
+            # align by leading limbs, then difference limb by limb
+            from scipy.optimize import linear_sum_assignment
+            r, c = linear_sum_assignment(np.abs(wg[None, :] - wr[:, None]))
+            dre = (w[0][c] - wm[0][r]) + (w[1][c] - wm[1][r])
+            dim = (w[2][c] - wm[2][r]) + (w[3][c] - wm[3][r])
+            err = np.hypot(dre, dim)
+            if kind == gs.CDD:
+                sc = s[c]     # s is ordered like diag(T) = values
+            else:
+                # match complex-path condition numbers to the real path's eigenvalues
+                wc = np.array([Tc[0, i, i] + 1j * Tc[2, i, i] for i in range(n)])
+                rr, cc = linear_sum_assignment(np.abs(wc[None, :] - wg[c][:, None]))
+                sc = s[cc]
+            tol = 1e3 * 2.0 ** -104 * anorm / np.maximum(sc, 1e-300)
+            assert np.all(err <= tol), (kind, n, b, float(np.max(err / tol)))
+
+
+def test_godunov_double_double(gs):
+    """Known-answer eigenvalues (test/real.jl:142-157, test/complex.jl:139-154) with the in-kernel double-double."""
+    G, vals, econd = godunov()
+    eps_dd = 2.0 ** -104
+    A = np.zeros((2, 7, 7), order="F")
+    A[0] = G
+    S = gs.gschur(A.view(gs.DDArray))
+    w = np.asarray(S.values)
+    wv = (w[0] + w[1]) + 1j * (w[2] + w[3])
+    assert np.allclose(csort(wv), vals, atol=3 * 100 * eps_dd * fnorm(G) * econd)
+    assert np.abs(csort(wv) - vals).max() < 1e-9      # double precision would be off by O(1)
+    C = np.zeros((4, 7, 7), order="F")
+    C[0] = G
+    S = gs.gschur(C.view(gs.CDDArray))
+    w = np.asarray(S.values)
+    wv = (w[0] + w[1]) + 1j * (w[2] + w[3])
+    assert np.abs(csort(wv) - vals).max() < 1e-9
+
+
+def _bulk_properties(A, S, kind):
+    """Size-independent invariants, vectorised over the whole batch: similarity preserves the trace and (Z unitary)
+    the Frobenius norm; T has the exact zero pattern; every matrix converged."""
+    n = A.shape[0]
+    assert not np.any(S.info)
+    tr = np.trace(A, axis1=0, axis2=1)
+    assert np.allclose(S.values.sum(axis=0), tr, rtol=0, atol=1e-11 * n)
+    fa = np.sqrt((np.abs(A) ** 2).sum(axis=(0, 1)))
+    ft = np.sqrt((np.abs(S.T) ** 2).sum(axis=(0, 1)))
+    assert np.allclose(fa, ft, rtol=1e-12)
+    fz = (np.abs(S.Z) ** 2).sum(axis=(0, 1))
+    assert np.allclose(fz, n, rtol=1e-12)
+    ii, jj = np.tril_indices(n, -1 if kind == 1 else -2)
+    assert not np.any(S.T[ii, jj, :])
+
+
+def test_full_size_cfg2(gs, O):
+    """BASELINE config 2: 16384 random 32x32 Float64 — invariants on all, full parity on a sample."""
+    rng = np.random.default_rng(1234 + 2)
+    A = np.asfortranarray(rng.random((32, 32, 16384)))
+    S = gs.gschur(A)
+    _bulk_properties(A, S, 0)
+    for b in (0, 1, 8191, 16383):
+        _check_one(O, A[:, :, b], S.T[:, :, b], S.Z[:, :, b], S.values[:, b], 0, 10, f"cfg2[{b}]")
+
+
+def test_full_size_cfg3_slice(gs, O):
+    """BASELINE config 3 shape (64x64 ComplexF64); one 8192-matrix shard (= the per-GPU share at 8 GPUs)."""
+    rng = np.random.default_rng(1234 + 3)
+    A = np.asfortranarray(rng.random((64, 64, 8192)) + 1j * rng.random((64, 64, 8192)))
+    S = gs.gschur(A)
+    _bulk_properties(A, S, 1)
+    for b in (0, 4095, 8191):
+        _check_one(O, A[:, :, b], S.T[:, :, b], S.Z[:, :, b], S.values[:, b], 1, 10, f"cfg3[{b}]")
+
+
+def test_cfg1_single_matrix(gs, O, golden):
+    """BASELINE config 1: one 64x64 random ComplexF64 matrix (the reference's CPU-runnable case)."""
+    A = np.asfortranarray(golden["c_cfg1_n64__A"])
+    S = gs.gschur(A)
+    _check_one(O, A, S.T, S.Z, S.values, 1, 10, "cfg1")
