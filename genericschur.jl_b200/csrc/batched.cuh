@@ -82,7 +82,7 @@ template <class R, int NT> GS_DEV R block_sum(R v, R* sred) {
 // ---- small reflectors used inside the QR sweeps ------------------------------------------------------------
 // Real xLARFG on a 2- or 3-vector held in registers (src/householder.jl:12-54).  Returns tau; v0 <- beta,
 // v1, v2 <- scaled tail.  The 2-norm of the tail and beta are formed with one scaled hypot.
-template <class R> GS_DEV R reflector_real_small(R& v0, R& v1, R& v2, int nr) {
+template <class R> GS_DEV R reflector_real_small_generic(R& v0, R& v1, R& v2, int nr) {
     const R zero = r_const<R>(0.0), one = r_const<R>(1.0);
     if (nr <= 1) return zero;
     if (nr == 2) v2 = zero;
@@ -113,8 +113,33 @@ template <class R> GS_DEV R reflector_real_small(R& v0, R& v1, R& v2, int nr) {
     return tau;
 }
 
+GS_DEV dd_t reflector_real_small(dd_t& v0, dd_t& v1, dd_t& v2, int nr) {
+    return reflector_real_small_generic<dd_t>(v0, v1, v2, nr);
+}
+// Float64 fast path: same quantities (beta = -sign(alpha) ||x||, tau = (beta - alpha)/beta, tail / (alpha - beta)),
+// computed on a copy scaled by an exact power of two with one fast sqrt and two fast reciprocals.
+GS_DEV double reflector_real_small(double& v0, double& v1, double& v2, int nr) {
+    if (nr <= 1) return 0.0;
+    if (nr == 2) v2 = 0.0;
+    if (v1 == 0.0 && v2 == 0.0) return 0.0;
+    const double w = fmax(fabs(v0), fmax(fabs(v1), fabs(v2)));
+    const double sfmin = 2.0 * 2.2250738585072014e-308 / 2.220446049250313e-16;
+    if (!(w >= sfmin && w <= 1e300)) return reflector_real_small_generic<double>(v0, v1, v2, nr);   // rare
+    double dn, up;
+    pow2_scales(w, dn, up);
+    const double a = v0 * dn, c = v1 * dn, d = v2 * dn;
+    const double q = fma(a, a, fma(c, c, d * d));
+    const double beta = -copysign(fast_sqrt(q), a);
+    const double tau = (beta - a) * fast_rcp(beta);
+    const double t = fast_rcp(a - beta);
+    v1 = c * t;
+    v2 = d * t;
+    v0 = beta * up;
+    return tau;
+}
+
 // Complex xLARFG on a 2-vector (src/householder.jl:56-102): beta real, tau complex.
-template <class R> GS_DEV cx<R> reflector_cplx2(cx<R>& v0, cx<R>& v1) {
+template <class R> GS_DEV cx<R> reflector_cplx2_generic(cx<R>& v0, cx<R>& v1) {
     const R zero = r_const<R>(0.0), one = r_const<R>(1.0);
     R ar = v0.re, ai = v0.im;
     if (v1.re == zero && v1.im == zero && ai == zero) return mk_cx<R>(zero, zero);
@@ -139,6 +164,29 @@ template <class R> GS_DEV cx<R> reflector_cplx2(cx<R>& v0, cx<R>& v1) {
     v1 = v1 * t;
     for (int j = 0; j < kount; ++j) beta = beta * sfmin;
     v0 = mk_cx<R>(beta, zero);
+    return tau;
+}
+
+GS_DEV cx<dd_t> reflector_cplx2(cx<dd_t>& v0, cx<dd_t>& v1) { return reflector_cplx2_generic<dd_t>(v0, v1); }
+GS_DEV cx<double> reflector_cplx2(cx<double>& v0, cx<double>& v1) {
+    const double ar = v0.re, ai = v0.im;
+    if (v1.re == 0.0 && v1.im == 0.0 && ai == 0.0) return mk_cx<double>(0.0, 0.0);
+    const double w = fmax(fmax(fabs(ar), fabs(ai)), fmax(fabs(v1.re), fabs(v1.im)));
+    const double sfmin = 2.2250738585072014e-308 / 2.220446049250313e-16;
+    if (!(w >= sfmin && w <= 1e300)) return reflector_cplx2_generic<double>(v0, v1);   // rare
+    double dn, up;
+    pow2_scales(w, dn, up);
+    const double a = ar * dn, b = ai * dn, c = v1.re * dn, d = v1.im * dn;
+    const double q = fma(a, a, fma(b, b, fma(c, c, d * d)));
+    const double beta = -copysign(fast_sqrt(q), a);
+    const double rb = fast_rcp(beta);
+    cx<double> tau = mk_cx<double>((beta - a) * rb, -b * rb);
+    // 1/(alpha - beta) = conj(alpha - beta) / |alpha - beta|^2; |a - beta| = |a| + ||x|| >= 1 on the scaled copy
+    const double amb = a - beta;
+    const double rm = fast_rcp(fma(amb, amb, b * b));
+    const double tr = amb * rm, ti = -b * rm;
+    v1 = mk_cx<double>(c * tr - d * ti, c * ti + d * tr);
+    v0 = mk_cx<double>(beta * up, 0.0);
     return tau;
 }
 

@@ -1,0 +1,1001 @@
+// Warp-specialised QR-iteration stage for Float64 / ComplexF64 matrices with n <= 64.
+//
+// The Francis sweep is a serial chain: reflector k+1 cannot be formed before reflector k has been applied to
+// the entries next to the diagonal.  Everything else — the far columns of H and the whole of Z — only needs the
+// reflectors, not the other way round.  This stage therefore splits the CTA in two roles:
+//
+//   * the H-warp (warp 0) owns the Hessenberg matrix.  Lane l owns columns and rows l+1, l+33 (CPL = 2).  It keeps
+//     the running entries of its columns (left update) and rows (right update) in registers ("carries"), so a
+//     bulge step costs one shared-memory load and one store per owned column/row instead of 2-3 each, and the
+//     only synchronisation on the critical path is __syncwarp.  Lanes on the diagonal publish / refresh their
+//     carries through shared memory, which is also where the next reflector's vector is picked up.
+//   * the Z-warp (warp 1) applies the reflectors to the Schur vectors.  It receives them a sweep at a time through
+//     a double-buffered record in shared memory (named barriers full[2] / empty[2]) and streams them through
+//     carry registers as well (one load + one store per row and step).  It never blocks the H-warp unless it
+//     falls two sweeps behind.
+//
+// The arithmetic per reflector application and every decision rule are those of batched.cuh (and of the
+// reference, src/GenericSchur.jl:194-335, 374-504, 513-699, 837-952); only the schedule differs.
+#pragma once
+#include "batched.cuh"
+
+namespace gs {
+
+enum { ZOP_REFL = 1, ZOP_SCALE = 2, ZOP_REFL3 = 3, ZOP_REFL2 = 4, ZOP_GIVENS = 5 };
+
+template <bool CPLX> struct zop_t;
+template <> struct __align__(16) zop_t<true> {   // 48 B
+    int op, k, k2, pad;
+    double a[4];   // REFL: tau1.re, tau1.im, v2.re, v2.im ; SCALE: t.re, t.im (columns k..k2)
+};
+template <> struct __align__(16) zop_t<false> {  // 32 B
+    int op, k;
+    double a[3];   // REFL3: tau1, v2, v3 ; REFL2: tau1, v2 ; GIVENS: cs, sn (columns k, k+1)
+};
+
+struct zring_hdr {
+    int count[2];
+    int end[2];
+};
+
+// named barriers with immediate ids (a register id would make ptxas reserve all 16 barriers per CTA)
+enum { BAR_FULL0 = 1, BAR_EMPTY0 = 3 };
+template <int ID> GS_DEV void bar_sync_imm() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
+template <int ID> GS_DEV void bar_arrive_imm() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
+GS_DEV void named_bar_sync(int id, int) {
+    switch (id) {
+        case 1: bar_sync_imm<1>(); break;
+        case 2: bar_sync_imm<2>(); break;
+        case 3: bar_sync_imm<3>(); break;
+        default: bar_sync_imm<4>(); break;
+    }
+}
+GS_DEV void named_bar_arrive(int id, int) {
+    switch (id) {
+        case 1: bar_arrive_imm<1>(); break;
+        case 2: bar_arrive_imm<2>(); break;
+        case 3: bar_arrive_imm<3>(); break;
+        default: bar_arrive_imm<4>(); break;
+    }
+}
+
+template <class T, int CPL> struct FastSolver {
+    typedef typename etraits<T>::real R;
+    typedef cx<R> C;
+    static constexpr bool CPLX = etraits<T>::is_complex;
+    typedef zop_t<CPLX> ZOp;
+
+    int n, ld, lane, cap;
+    T* H;
+    T* Z;
+    C* sW;
+    ZOp* ring;        // [2][cap]
+    zring_hdr* hdr;
+    bool wantZ;
+    unsigned* stp;
+    BatchedSolver<T, 32> B;   // shared decision rules (split tests, first column), run by the H-warp alone
+    // producer state (uniform across the H-warp)
+    int sidx, cnt;
+
+#define HH(i, j) H[((i)-1) + ((j)-1) * ld]
+#define ZZ(i, j) Z[((i)-1) + ((j)-1) * ld]
+
+    // ------------------------------------------------------------------------------------------------
+    // producer side of the Z ring
+    // ------------------------------------------------------------------------------------------------
+    GS_DEV void begin_buffer() {
+        if (!wantZ) return;
+        if (sidx >= 2) named_bar_sync(BAR_EMPTY0 + (sidx & 1), 64);
+        cnt = 0;
+    }
+    GS_DEV void publish(int end) {
+        if (!wantZ) return;
+        const int b = sidx & 1;
+        if (lane == 0) {
+            hdr->count[b] = cnt;
+            hdr->end[b] = end;
+        }
+        __syncwarp();
+        named_bar_arrive(BAR_FULL0 + b, 64);
+        sidx += 1;
+    }
+    GS_DEV void ensure_space(int m) {
+        if (!wantZ) return;
+        if (cnt + m > cap) {
+            publish(0);
+            begin_buffer();
+        }
+    }
+    GS_DEV ZOp* slot() { return ring + (sidx & 1) * cap + cnt; }
+    GS_DEV void finish_ring() {
+        if (!wantZ) return;
+        publish(1);
+        // balance the outstanding "empty" arrivals of the last two buffers
+        const int last = sidx - 1;
+        for (int c = (last - 1 < 0 ? 0 : last - 1); c <= last; ++c) named_bar_sync(BAR_EMPTY0 + (c & 1), 64);
+    }
+
+    // ================================================================================================
+    // complex single shift
+    // ================================================================================================
+    GS_DEV void emit_refl_c(int k, const C& tau1, const C& v2) {
+        if (!wantZ) return;
+        ensure_space(1);
+        if (lane == 0) {
+            ZOp* e = slot();
+            e->op = ZOP_REFL;
+            e->k = k;
+            e->k2 = k;
+            e->a[0] = tau1.re;
+            e->a[1] = tau1.im;
+            e->a[2] = v2.re;
+            e->a[3] = v2.im;
+        }
+        cnt += 1;
+    }
+    GS_DEV void emit_scale_c(int j0, int j1, const C& t) {
+        if (!wantZ || j1 < j0) return;
+        ensure_space(1);
+        if (lane == 0) {
+            ZOp* e = slot();
+            e->op = ZOP_SCALE;
+            e->k = j0;
+            e->k2 = j1;
+            e->a[0] = t.re;
+            e->a[1] = t.im;
+            e->a[2] = 0.0;
+            e->a[3] = 0.0;
+        }
+        cnt += 1;
+    }
+
+    GS_DEV void sweep_complex(const C& shift, int istart, int iend) {
+        const R zero = r_const<R>(0.0), one = r_const<R>(1.0);
+        const R ulp = rtraits<R>::eps();
+        int istart1 = 0;
+        for (int base = iend - 1; base >= istart + 1 && !istart1; base -= 32) {
+            int mm = base - lane;
+            bool hit = false;
+            if (mm >= istart + 1) {
+                C h11 = HH(mm, mm), h22 = HH(mm + 1, mm + 1);
+                C h11s = h11 - shift;
+                R h21 = HH(mm + 1, mm).re;
+                R s = abs1(h11s) + r_abs(h21);
+                h11s = mk_cx<R>(h11s.re / s, h11s.im / s);
+                h21 = h21 / s;
+                R h10 = HH(mm, mm - 1).re;
+                hit = r_abs(h10) * r_abs(h21) <= ulp * (abs1(h11s) * (abs1(h11) + abs1(h22)));
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) istart1 = base - (__ffs(m) - 1);
+        }
+        if (!istart1) istart1 = istart;
+        const int k0 = istart1;
+        C v0, v1;
+        {
+            C h11s = HH(k0, k0) - shift;
+            R h21 = HH(k0 + 1, k0).re;
+            R s = abs1(h11s) + r_abs(h21);
+            v0 = mk_cx<R>(h11s.re / s, h11s.im / s);
+            v1 = mk_cx<R>(h21 / s, zero);
+        }
+        // carries: cL[s] = H[k, j] for the owned column j >= k;  dR[s] = H[i, k] for the owned row i < k
+        C cL[CPL], dR[CPL];
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+            const int j = lane + 1 + 32 * s;
+            cL[s] = (j >= k0 && j <= n) ? HH(k0, j) : mk_cx<R>(zero, zero);
+            dR[s] = (j < k0) ? HH(j, k0) : mk_cx<R>(zero, zero);
+        }
+        for (int k = k0; k <= iend - 1; ++k) {
+            if (k > k0) {
+                v0 = HH(k, k - 1);
+                v1 = HH(k + 1, k - 1);
+            }
+            const C tau1 = reflector_cplx2(v0, v1);
+            stp[1] += 1;
+            const C v2 = v1, v2c = cconj(v1), tau1c = cconj(tau1);
+            const R tau2 = (tau1 * v2).re;
+            emit_refl_c(k, tau1, v2);
+            // ---- left update of rows k, k+1: owned columns j >= k ----
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const int j = lane + 1 + 32 * s;
+                if (j >= k && j <= n) {
+                    const C b = HH(k + 1, j);
+                    const C ss = tau1c * cL[s] + tau2 * b;
+                    HH(k, j) = cL[s] - ss;
+                    cL[s] = b - ss * v2;
+                    if (j <= k + 1) HH(k + 1, j) = cL[s];   // diagonal columns publish their carry
+                }
+            }
+            __syncwarp();
+            // ---- right update of columns k, k+1: owned rows i <= min(k+2, iend) ----
+            const int jmax = (k + 2 < iend) ? k + 2 : iend;
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const int i = lane + 1 + 32 * s;
+                if (i <= jmax) {
+                    const C d = (i >= k) ? HH(i, k) : dR[s];
+                    const C e = HH(i, k + 1);
+                    const C ss = tau1 * d + tau2 * e;
+                    HH(i, k) = d - ss;
+                    dR[s] = e - ss * v2c;
+                    if (i >= k + 1) HH(i, k + 1) = dR[s];
+                }
+            }
+            if (lane == 0 && k > k0) {
+                HH(k, k - 1) = v0;
+                HH(k + 1, k - 1) = mk_cx<R>(zero, zero);
+            }
+            __syncwarp();
+            // column k+1's running entry H[k+1,k+1] was just rewritten by its own lane as row k+1
+#pragma unroll
+            for (int s = 0; s < CPL; ++s)
+                if (lane + 1 + 32 * s == k + 1) cL[s] = dR[s];
+
+            if (k == k0 && k0 > istart) {
+                // late start (src/GenericSchur.jl:461-482): flush the carries, rescale in shared memory, reload
+#pragma unroll
+                for (int s = 0; s < CPL; ++s) {
+                    const int j = lane + 1 + 32 * s;
+                    if (j >= k + 2 && j <= n) HH(k + 1, j) = cL[s];
+                    if (j <= k) HH(j, k + 1) = dR[s];
+                }
+                __syncwarp();
+                C t = mk_cx<R>(one, zero) - tau1;
+                R at = c_abs(t);
+                t = mk_cx<R>(t.re / at, t.im / at);
+                const C tc = cconj(t);
+                if (lane == 0) {
+                    HH(k0 + 1, k0) = HH(k0 + 1, k0) * tc;
+                    if (k0 + 2 <= iend) HH(k0 + 2, k0 + 1) = HH(k0 + 2, k0 + 1) * t;
+                }
+                __syncwarp();
+                for (int j = k0; j <= iend; ++j) {
+                    if (j == k0 + 1) continue;
+                    for (int c = j + 1 + lane; c <= n; c += 32) HH(j, c) = HH(j, c) * t;
+                    for (int r = 1 + lane; r <= j - 1; r += 32) HH(r, j) = HH(r, j) * tc;
+                    __syncwarp();
+                }
+                emit_scale_c(k0, k0, tc);
+                emit_scale_c(k0 + 2, iend, tc);
+#pragma unroll
+                for (int s = 0; s < CPL; ++s) {
+                    const int j = lane + 1 + 32 * s;
+                    cL[s] = (j >= k + 1 && j <= n) ? HH(k + 1, j) : mk_cx<R>(zero, zero);
+                    dR[s] = (j < k + 1) ? HH(j, k + 1) : mk_cx<R>(zero, zero);
+                }
+            }
+        }
+        // ---- flush the carries left after the last step (k = iend-1) ----
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+            const int j = lane + 1 + 32 * s;
+            if (j >= iend + 1 && j <= n) HH(iend, j) = cL[s];
+            if (j <= iend - 1) HH(j, iend) = dR[s];
+        }
+        __syncwarp();
+        // ---- make the tail sub-diagonal real (src/GenericSchur.jl:486-500) ----
+        C t = HH(iend, iend - 1);
+        if (t.im != zero) {
+            R rt = c_abs(t);
+            t = mk_cx<R>(t.re / rt, t.im / rt);
+            const C tc = cconj(t);
+            for (int c = iend + 1 + lane; c <= n; c += 32) HH(iend, c) = HH(iend, c) * tc;
+            for (int r = 1 + lane; r <= iend - 1; r += 32) HH(r, iend) = HH(r, iend) * t;
+            emit_scale_c(iend, iend, t);
+            __syncwarp();
+            if (lane == 0) HH(iend, iend - 1) = mk_cx<R>(rt, zero);
+        }
+        __syncwarp();
+    }
+
+    GS_DEV int qr_complex(int maxiter, unsigned* st) {
+        stp = st;
+        const R zero = r_const<R>(0.0), half = r_const<R>(0.5), threeq = r_const<R>(0.75);
+        const R ulp = rtraits<R>::eps();
+        const R smallnum = r_safemin<R>() * (r_const<R>((double)n) / ulp);
+        const int maxinner = 30 * n;
+        int istart = 1, iend = n, it = 0;
+        sidx = 0;
+        cnt = 0;
+        begin_buffer();
+        while (iend >= 1) {
+            istart = 1;
+            for (int its = 0; its <= maxinner; ++its) {
+                it += 1;
+                if (it > maxiter) {
+                    st[3] = it;
+                    finish_ring();
+                    return iend;
+                }
+                int found = 0;
+                for (int base = iend - 1; base >= istart && !found; base -= 32) {
+                    int c = base - lane;
+                    bool hit = (c >= istart) ? B.split_test_c(c, smallnum, ulp) : false;
+                    unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (m) found = base - (__ffs(m) - 1);
+                }
+                if (found) istart = found + 1;
+                __syncwarp();
+                if (istart > 1 && lane == 0) HH(istart, istart - 1) = mk_cx<R>(zero, zero);
+                __syncwarp();
+                if (istart >= iend) {
+                    iend -= 1;
+                    break;
+                }
+                C t;
+                if (its % 30 == 10) {
+                    R s = threeq * r_abs(HH(istart + 1, istart).re);
+                    t = HH(istart, istart);
+                    t.re = t.re + s;
+                    st[2] += 1;
+                } else if (its % 30 == 20) {
+                    R s = threeq * r_abs(HH(iend, iend - 1).re);
+                    t = HH(iend, iend);
+                    t.re = t.re + s;
+                    st[2] += 1;
+                } else {
+                    t = HH(iend, iend);
+                    C u = c_sqrt(HH(iend - 1, iend)) * c_sqrt(HH(iend, iend - 1));
+                    R s = abs1(u);
+                    if (s != zero) {
+                        C x = half * (HH(iend - 1, iend - 1) - t);
+                        R sx = abs1(x);
+                        s = r_max(s, sx);
+                        C xs = mk_cx<R>(x.re / s, x.im / s), us = mk_cx<R>(u.re / s, u.im / s);
+                        C y = s * c_sqrt(xs * xs + us * us);
+                        if (sx > zero) {
+                            if ((x.re / sx) * y.re + (x.im / sx) * y.im < zero) y = -y;
+                        }
+                        t = t - u * (u / (x + y));
+                    }
+                }
+                st[0] += 1;
+                sweep_complex(t, istart, iend);
+                // hand the sweep's reflectors to the Z-warp
+                publish(0);
+                begin_buffer();
+            }
+        }
+        st[3] = it;
+        finish_ring();
+        return 0;
+    }
+
+    // ================================================================================================
+    // real double shift
+    // ================================================================================================
+    GS_DEV void emit_r(int op, int k, const R& a0, const R& a1, const R& a2) {
+        if (!wantZ) return;
+        ensure_space(1);
+        if (lane == 0) {
+            ZOp* e = slot();
+            e->op = op;
+            e->k = k;
+            e->a[0] = a0;
+            e->a[1] = a1;
+            e->a[2] = a2;
+        }
+        cnt += 1;
+    }
+
+    GS_DEV void sweep_real(const R& r1r, const R& r1i, const R& r2r, const R& r2i, int istart, int iend) {
+        const R zero = r_const<R>(0.0), one = r_const<R>(1.0);
+        const R eps = rtraits<R>::eps();
+        int mx = 0;
+        for (int base = iend - 2; base >= istart + 1 && !mx; base -= 32) {
+            int m = base - lane;
+            bool hit = false;
+            if (m >= istart + 1) {
+                R a0, a1, a2;
+                B.first_column_r(m, r1r, r1i, r2r, r2i, a0, a1, a2);
+                hit = r_abs(HH(m, m - 1)) * (r_abs(a1) + r_abs(a2)) <=
+                      eps * r_abs(a0) * (r_abs(HH(m - 1, m - 1)) + r_abs(HH(m, m)) + r_abs(HH(m + 1, m + 1)));
+            }
+            unsigned msk = __ballot_sync(0xffffffffu, hit);
+            if (msk) mx = base - (__ffs(msk) - 1);
+        }
+        if (!mx) mx = istart;
+        R v0, v1, v2;
+        B.first_column_r(mx, r1r, r1i, r2r, r2i, v0, v1, v2);
+        // carries: (cL1, cL2) = H[k, j], H[k+1, j] for owned columns j >= k;  (dR1, dR2) = H[i, k], H[i, k+1], rows i < k
+        R cL1[CPL], cL2[CPL], dR1[CPL], dR2[CPL];
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+            const int j = lane + 1 + 32 * s;
+            const bool c = (j >= mx && j <= n), r = (j < mx);
+            cL1[s] = c ? HH(mx, j) : zero;
+            cL2[s] = c ? HH(mx + 1, j) : zero;
+            dR1[s] = r ? HH(j, mx) : zero;
+            dR2[s] = r ? HH(j, mx + 1) : zero;
+        }
+        int k = mx;
+        for (; k <= iend - 2; ++k) {   // three-row reflectors
+            if (k > mx) {
+                v0 = HH(k, k - 1);
+                v1 = HH(k + 1, k - 1);
+                v2 = HH(k + 2, k - 1);
+            }
+            const R tau1 = reflector_real_small(v0, v1, v2, 3);
+            stp[1] += 1;
+            const R tau2 = tau1 * v1, tau3 = tau1 * v2;
+            emit_r(ZOP_REFL3, k, tau1, v1, v2);
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const int j = lane + 1 + 32 * s;
+                if (j >= k && j <= n) {
+                    const R b = HH(k + 2, j);
+                    const R ss = cL1[s] + v1 * cL2[s] + v2 * b;
+                    HH(k, j) = cL1[s] - ss * tau1;
+                    cL1[s] = cL2[s] - ss * tau2;
+                    cL2[s] = b - ss * tau3;
+                    if (j <= k + 2) {
+                        HH(k + 1, j) = cL1[s];
+                        HH(k + 2, j) = cL2[s];
+                    }
+                }
+            }
+            __syncwarp();
+            const int jmax = (k + 3 < iend) ? k + 3 : iend;
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const int i = lane + 1 + 32 * s;
+                if (i <= jmax) {
+                    R d1, d2;
+                    if (i >= k) {
+                        d1 = HH(i, k);
+                        d2 = HH(i, k + 1);
+                    } else {
+                        d1 = dR1[s];
+                        d2 = dR2[s];
+                    }
+                    const R e = HH(i, k + 2);
+                    const R ss = d1 + v1 * d2 + v2 * e;
+                    HH(i, k) = d1 - ss * tau1;
+                    dR1[s] = d2 - ss * tau2;
+                    dR2[s] = e - ss * tau3;
+                    if (i >= k + 1) {
+                        HH(i, k + 1) = dR1[s];
+                        HH(i, k + 2) = dR2[s];
+                    }
+                }
+            }
+            if (lane == 0) {
+                if (k > mx) {
+                    HH(k, k - 1) = v0;
+                    HH(k + 1, k - 1) = zero;
+                    HH(k + 2, k - 1) = zero;
+                } else if (mx > istart) {
+                    HH(k, k - 1) = HH(k, k - 1) * (one - tau1);
+                }
+            }
+            __syncwarp();
+            // columns k+1, k+2 were rewritten by the right update in rows k+1, k+2: refresh their carries
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const int j = lane + 1 + 32 * s;
+                if (j == k + 1 || j == k + 2) {
+                    cL1[s] = HH(k + 1, j);
+                    cL2[s] = HH(k + 2, j);
+                }
+            }
+        }
+        // ---- last step: two-row reflector at k = iend-1; everything is written back ----
+        {
+            v0 = HH(k, k - 1);
+            v1 = HH(k + 1, k - 1);
+            v2 = zero;
+            const R tau1 = reflector_real_small(v0, v1, v2, 2);
+            stp[1] += 1;
+            const R tau2 = tau1 * v1;
+            emit_r(ZOP_REFL2, k, tau1, v1, zero);
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const int j = lane + 1 + 32 * s;
+                if (j >= k && j <= n) {
+                    const R ss = cL1[s] + v1 * cL2[s];
+                    HH(k, j) = cL1[s] - ss * tau1;
+                    HH(k + 1, j) = cL2[s] - ss * tau2;
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const int i = lane + 1 + 32 * s;
+                if (i <= iend) {
+                    R d1, d2;
+                    if (i >= k) {
+                        d1 = HH(i, k);
+                        d2 = HH(i, k + 1);
+                    } else {
+                        d1 = dR1[s];
+                        d2 = dR2[s];
+                    }
+                    const R ss = d1 + v1 * d2;
+                    HH(i, k) = d1 - ss * tau1;
+                    HH(i, k + 1) = d2 - ss * tau2;
+                }
+            }
+            if (lane == 0) {
+                HH(k, k - 1) = v0;
+                HH(k + 1, k - 1) = zero;
+            }
+            __syncwarp();
+        }
+    }
+
+    GS_DEV int qr_real(int maxiter, unsigned* st) {
+        stp = st;
+        const R zero = r_const<R>(0.0);
+        const R eps = rtraits<R>::eps();
+        const R smallnum = rtraits<R>::floatmin() * (r_const<R>((double)n) / eps);
+        const R threeq = r_const<R>(0.75), m7_16 = r_const<R>(-0.4375);
+        int istart = 1, iend = n, iwcur = n, iter = 0;
+        sidx = 0;
+        cnt = 0;
+        begin_buffer();
+        while (iend >= 1) {
+            istart = 1;
+            int iterqr = 0;
+            while (true) {
+                iter += 1;
+                if (iter > maxiter) {
+                    st[3] = iter;
+                    finish_ring();
+                    return iend;
+                }
+                int found = 0;
+                for (int base = iend; base >= istart + 1 && !found; base -= 32) {
+                    int k = base - lane;
+                    bool hit = (k >= istart + 1) ? B.split_test_r(k, smallnum, eps) : false;
+                    unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (m) found = base - (__ffs(m) - 1);
+                }
+                istart = found ? found : 1;
+                __syncwarp();
+                if (istart > 1 && lane == 0) HH(istart, istart - 1) = zero;
+                __syncwarp();
+                if (istart >= iend - 1) break;
+                iterqr += 1;
+                R H11, H12, H21, H22;
+                if (iterqr == 10) {
+                    R s = r_abs(HH(istart + 1, istart)) + r_abs(HH(istart + 2, istart + 1));
+                    H11 = threeq * s + HH(istart, istart);
+                    H12 = m7_16 * s;
+                    H21 = s;
+                    H22 = H11;
+                    st[2] += 1;
+                } else if (iterqr == 20) {
+                    R s = r_abs(HH(iend, iend - 1)) + r_abs(HH(iend - 1, iend - 2));
+                    H11 = threeq * s + HH(iend, iend);
+                    H12 = m7_16 * s;
+                    H21 = s;
+                    H22 = H11;
+                    st[2] += 1;
+                } else {
+                    H11 = HH(iend - 1, iend - 1);
+                    H21 = HH(iend, iend - 1);
+                    H12 = HH(iend - 1, iend);
+                    H22 = HH(iend, iend);
+                }
+                R s = r_abs(H11) + r_abs(H12) + r_abs(H21) + r_abs(H22);
+                R r1r = zero, r2r = zero, r1i = zero, r2i = zero;
+                if (!(s == zero)) {
+                    H11 = H11 / s;
+                    H12 = H12 / s;
+                    H21 = H21 / s;
+                    H22 = H22 / s;
+                    R tr = (H11 + H22) * r_const<R>(0.5);
+                    R d = (H11 - tr) * (H22 - tr) - H12 * H21;
+                    R rtd = r_sqrt(r_abs(d));
+                    if (d >= zero) {
+                        r1r = tr * s;
+                        r2r = r1r;
+                        r1i = rtd * s;
+                        r2i = -r1i;
+                    } else {
+                        r1r = tr + rtd;
+                        r2r = tr - rtd;
+                        if (r_abs(r1r - H22) <= r_abs(r2r - H22)) {
+                            r1r = r1r * s;
+                            r2r = r1r;
+                        } else {
+                            r2r = r2r * s;
+                            r1r = r2r;
+                        }
+                    }
+                }
+                st[0] += 1;
+                sweep_real(r1r, r1i, r2r, r2i, istart, iend);
+                publish(0);
+                begin_buffer();
+            }
+            if (istart >= iend) {
+                if (lane == 0) sW[iwcur - 1] = mk_cx<R>(HH(iend, iend), zero);
+                iwcur -= 1;
+            } else if (istart + 1 == iend) {
+                R a = HH(iend - 1, iend - 1), b = HH(iend - 1, iend), c = HH(iend, iend - 1), d = HH(iend, iend);
+                R cs, sn;
+                C w1, w2;
+                gs2x2(a, b, c, d, cs, sn, w1, w2);
+                if (lane == 0) {
+                    sW[iwcur - 1] = w2;
+                    sW[iwcur - 2] = w1;
+                }
+                iwcur -= 2;
+                emit_r(ZOP_GIVENS, iend - 1, cs, sn, zero);
+                __syncwarp();
+                for (int j = istart + lane; j <= n; j += 32) {
+                    R a1 = HH(iend - 1, j), a2 = HH(iend, j);
+                    HH(iend - 1, j) = cs * a1 + sn * a2;
+                    HH(iend, j) = -sn * a1 + cs * a2;
+                }
+                __syncwarp();
+                for (int r = 1 + lane; r <= iend; r += 32) {
+                    R a1 = HH(r, iend - 1), a2 = HH(r, iend);
+                    HH(r, iend - 1) = a1 * cs + a2 * sn;
+                    HH(r, iend) = -a1 * sn + a2 * cs;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    HH(iend - 1, iend - 1) = a;
+                    HH(iend - 1, iend) = b;
+                    HH(iend, iend - 1) = c;
+                    HH(iend, iend) = d;
+                    if (iend > 2) HH(iend - 1, iend - 2) = zero;
+                }
+                __syncwarp();
+            }
+            iend = istart - 1;
+        }
+        st[3] = iter;
+        finish_ring();
+        return 0;
+    }
+
+    // ================================================================================================
+    // consumer: the Z-warp
+    // ================================================================================================
+    GS_DEV void z_consumer() {
+        const R zero = r_const<R>(0.0);
+        for (int cidx = 0;; ++cidx) {
+            const int b = cidx & 1;
+            named_bar_sync(BAR_FULL0 + b, 64);
+            const int count = hdr->count[b];
+            const int end = hdr->end[b];
+            const ZOp* ops = ring + b * cap;
+            int i = 0;
+            while (i < count) {
+                const int op = ops[i].op;
+                if constexpr (CPLX) {
+                    if (op == ZOP_REFL) {
+                        int k = ops[i].k;
+                        C z0[CPL];
+#pragma unroll
+                        for (int s = 0; s < CPL; ++s) {
+                            const int r = lane + 1 + 32 * s;
+                            z0[s] = (r <= n) ? ZZ(r, k) : mk_cx<R>(zero, zero);
+                        }
+                        while (i < count && ops[i].op == ZOP_REFL && ops[i].k == k) {
+                            const C tau1 = mk_cx<R>(ops[i].a[0], ops[i].a[1]);
+                            const C v2 = mk_cx<R>(ops[i].a[2], ops[i].a[3]);
+                            const C v2c = cconj(v2);
+                            const R tau2 = (tau1 * v2).re;
+#pragma unroll
+                            for (int s = 0; s < CPL; ++s) {
+                                const int r = lane + 1 + 32 * s;
+                                if (r <= n) {
+                                    const C z1 = ZZ(r, k + 1);
+                                    const C ss = tau1 * z0[s] + tau2 * z1;
+                                    ZZ(r, k) = z0[s] - ss;
+                                    z0[s] = z1 - ss * v2c;
+                                }
+                            }
+                            k += 1;
+                            i += 1;
+                        }
+#pragma unroll
+                        for (int s = 0; s < CPL; ++s) {
+                            const int r = lane + 1 + 32 * s;
+                            if (r <= n) ZZ(r, k) = z0[s];
+                        }
+                    } else {   // ZOP_SCALE
+                        const C t = mk_cx<R>(ops[i].a[0], ops[i].a[1]);
+                        for (int j = ops[i].k; j <= ops[i].k2; ++j) {
+#pragma unroll
+                            for (int s = 0; s < CPL; ++s) {
+                                const int r = lane + 1 + 32 * s;
+                                if (r <= n) ZZ(r, j) = ZZ(r, j) * t;
+                            }
+                        }
+                        i += 1;
+                    }
+                } else {
+                    if (op == ZOP_REFL3) {
+                        int k = ops[i].k;
+                        R z1[CPL], z2[CPL];
+#pragma unroll
+                        for (int s = 0; s < CPL; ++s) {
+                            const int r = lane + 1 + 32 * s;
+                            z1[s] = (r <= n) ? ZZ(r, k) : zero;
+                            z2[s] = (r <= n) ? ZZ(r, k + 1) : zero;
+                        }
+                        while (i < count && ops[i].op == ZOP_REFL3 && ops[i].k == k) {
+                            const R tau1 = ops[i].a[0], v2 = ops[i].a[1], v3 = ops[i].a[2];
+                            const R tau2 = tau1 * v2, tau3 = tau1 * v3;
+#pragma unroll
+                            for (int s = 0; s < CPL; ++s) {
+                                const int r = lane + 1 + 32 * s;
+                                if (r <= n) {
+                                    const R z3 = ZZ(r, k + 2);
+                                    const R ss = z1[s] + v2 * z2[s] + v3 * z3;
+                                    ZZ(r, k) = z1[s] - ss * tau1;
+                                    z1[s] = z2[s] - ss * tau2;
+                                    z2[s] = z3 - ss * tau3;
+                                }
+                            }
+                            k += 1;
+                            i += 1;
+                        }
+#pragma unroll
+                        for (int s = 0; s < CPL; ++s) {
+                            const int r = lane + 1 + 32 * s;
+                            if (r <= n) {
+                                ZZ(r, k) = z1[s];
+                                ZZ(r, k + 1) = z2[s];
+                            }
+                        }
+                    } else if (op == ZOP_REFL2) {
+                        const int k = ops[i].k;
+                        const R tau1 = ops[i].a[0], v2 = ops[i].a[1];
+                        const R tau2 = tau1 * v2;
+#pragma unroll
+                        for (int s = 0; s < CPL; ++s) {
+                            const int r = lane + 1 + 32 * s;
+                            if (r <= n) {
+                                const R a = ZZ(r, k), b2 = ZZ(r, k + 1);
+                                const R ss = a + v2 * b2;
+                                ZZ(r, k) = a - ss * tau1;
+                                ZZ(r, k + 1) = b2 - ss * tau2;
+                            }
+                        }
+                        i += 1;
+                    } else {   // ZOP_GIVENS
+                        const int k = ops[i].k;
+                        const R cs = ops[i].a[0], sn = ops[i].a[1];
+#pragma unroll
+                        for (int s = 0; s < CPL; ++s) {
+                            const int r = lane + 1 + 32 * s;
+                            if (r <= n) {
+                                const R a1 = ZZ(r, k), a2 = ZZ(r, k + 1);
+                                ZZ(r, k) = a1 * cs + a2 * sn;
+                                ZZ(r, k + 1) = -a1 * sn + a2 * cs;
+                            }
+                        }
+                        i += 1;
+                    }
+                }
+            }
+            named_bar_arrive(BAR_EMPTY0 + b, 64);
+            if (end) break;
+        }
+    }
+#undef HH
+#undef ZZ
+};
+
+// =================================================================================================
+// kernel: one matrix per 64-thread CTA.  Load / scale / Hessenberg / form-Q / store reuse the block-wide code of
+// batched.cuh (all 64 threads); the QR stage runs warp-specialised.
+// =================================================================================================
+template <class T> struct fast_smem_layout {
+    typedef smem_layout<T> L;
+    typedef zop_t<etraits<T>::is_complex> ZOp;
+    __host__ __device__ static int cap(int n) { return n + 8; }
+    __host__ __device__ static size_t off_ring(int n) { return L::up16(L::off_mbar(n) + 16); }
+    __host__ __device__ static size_t off_hdr(int n) { return off_ring(n) + L::up16(2 * (size_t)cap(n) * sizeof(ZOp)); }
+    __host__ __device__ static size_t bytes(int n) { return off_hdr(n) + L::up16(sizeof(zring_hdr)); }
+};
+
+template <class T, int CPL>
+__global__ void __launch_bounds__(64) gschur_fast_kernel(BatchedParams p) {
+    typedef typename etraits<T>::real R;
+    typedef cx<R> C;
+    constexpr bool CPLX = etraits<T>::is_complex;
+    constexpr int NT = 64;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = p.n, ld = smem_layout<T>::ld(n);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    typedef smem_layout<T> L;
+    typedef fast_smem_layout<T> FL;
+
+    BatchedSolver<T, NT> S;
+    S.n = n;
+    S.ld = ld;
+    S.tid = tid;
+    S.lane = lane;
+    S.H = reinterpret_cast<T*>(smem_raw);
+    S.Z = reinterpret_cast<T*>(smem_raw + L::off_Z(n));
+    S.sTau = reinterpret_cast<T*>(smem_raw + L::off_tau(n));
+    S.sW = reinterpret_cast<C*>(smem_raw + L::off_w(n));
+    S.sRed = reinterpret_cast<R*>(smem_raw + L::off_red(n));
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L::off_mbar(n));
+    __shared__ long long s_next;
+    __shared__ int s_info;
+    __shared__ unsigned s_stats[4];
+    S.wantZ = (p.Z != nullptr);
+
+    FastSolver<T, CPL> F;
+    F.n = n;
+    F.ld = ld;
+    F.lane = lane;
+    F.cap = FL::cap(n);
+    F.H = S.H;
+    F.Z = S.Z;
+    F.sW = S.sW;
+    F.ring = reinterpret_cast<typename FastSolver<T, CPL>::ZOp*>(smem_raw + FL::off_ring(n));
+    F.hdr = reinterpret_cast<zring_hdr*>(smem_raw + FL::off_hdr(n));
+    F.wantZ = S.wantZ;
+    F.B.n = n;
+    F.B.ld = ld;
+    F.B.tid = lane;
+    F.B.lane = lane;
+    F.B.H = S.H;
+    F.B.Z = S.Z;
+    F.B.sTau = S.sTau;
+    F.B.sW = S.sW;
+    F.B.sRed = S.sRed;
+    F.B.wantZ = S.wantZ;
+
+    if (tid == 0) mbar_init(mbar, 1);
+    __syncthreads();
+    uint32_t parity = 0;
+    const size_t mat_bytes = (size_t)n * n * sizeof(T);
+    const bool dense = (p.lda == n);
+
+    for (;;) {
+        if (tid == 0) s_next = (long long)atomicAdd(p.counter, 1ULL);
+        __syncthreads();
+        const long long b = s_next;
+        __syncthreads();
+        if (b >= p.batch) break;
+
+        T* gA = reinterpret_cast<T*>(p.A) + b * p.strideA;
+        T* gZ = S.wantZ ? reinterpret_cast<T*>(p.Z) + b * p.strideZ : nullptr;
+        const R zero = r_const<R>(0.0);
+
+        const bool use_tma = dense && (mat_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(gA) & 15) == 0);
+        if (use_tma) {
+            if (tid == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(mbar, (uint32_t)mat_bytes);
+                tma_bulk_g2s(S.Z, gA, (uint32_t)mat_bytes, mbar);
+            }
+            mbar_wait(mbar, parity);
+            parity ^= 1;
+            for (int e = tid; e < n * n; e += NT) {
+                int i = e % n, j = e / n;
+                S.H[i + j * ld] = S.Z[e];
+            }
+        } else {
+            for (int e = tid; e < n * n; e += NT) {
+                int i = e % n, j = e / n;
+                S.H[i + j * ld] = gA[i + (size_t)j * p.lda];
+            }
+        }
+        __syncthreads();
+
+        int info = 0;
+        bool scaled = false;
+        R cscale = r_const<R>(1.0), anrm = r_const<R>(1.0);
+        if (p.flags & F_HESS_INPUT) {
+            if (S.wantZ)
+                for (int e = tid; e < n * n; e += NT) {
+                    int i = e % n, j = e / n;
+                    S.Z[i + j * ld] = gZ[i + (size_t)j * p.ldz];
+                }
+            if (CPLX && (p.flags & F_CHECK_SUBDIAG)) {
+                int bad = 0;
+                if constexpr (CPLX) {
+                    for (int j = 1 + tid; j <= n - 1; j += NT)
+                        if (S.H[j + (j - 1) * ld].im != zero) bad = 1;
+                }
+                bad = __syncthreads_or(bad);
+                if (bad) info = -4;
+            }
+            __syncthreads();
+        } else {
+            if (p.scale) scaled = S.scale_in(cscale, anrm);
+            S.hessenberg();
+            if (S.wantZ) S.form_q();
+        }
+        if (info == 0) {
+            S.zero_below_subdiag();
+            const int maxiter = p.maxiter > 0 ? p.maxiter : 100 * n;
+            if (warp == 0) {
+                unsigned st[4] = {0u, 0u, 0u, 0u};
+                int rc;
+                if constexpr (CPLX) rc = F.qr_complex(maxiter, st);
+                else rc = F.qr_real(maxiter, st);
+                if (lane == 0) {
+                    s_info = rc;
+                    s_stats[0] = st[0];
+                    s_stats[1] = st[1];
+                    s_stats[2] = st[2];
+                    s_stats[3] = st[3];
+                }
+            } else if (S.wantZ) {
+                F.z_consumer();
+            }
+            __syncthreads();
+            info = s_info;
+        } else if (tid == 0) {
+            s_stats[0] = s_stats[1] = s_stats[2] = s_stats[3] = 0u;
+        }
+        __syncthreads();
+
+        if (scaled) {
+            safescale_apply<T, R, NT>(cscale, anrm, [&](R mul) {
+                for (int e = tid; e < n * n; e += NT) {
+                    int i = e % n, j = e / n;
+                    S.H[i + j * ld] = e_scale(S.H[i + j * ld], mul);
+                }
+                if (!CPLX)
+                    for (int e = tid; e < n; e += NT) S.sW[e] = mk_cx<R>(S.sW[e].re * mul, S.sW[e].im * mul);
+            });
+            __syncthreads();
+        }
+        for (int e = tid; e < n * n; e += NT) {
+            int i = e % n, j = e / n;
+            T v = S.H[i + j * ld];
+            bool keep = CPLX ? (i <= j) : (i <= j + 1);
+            gA[i + (size_t)j * p.lda] = keep ? v : e_zero<T>();
+            if (S.wantZ) gZ[i + (size_t)j * p.ldz] = S.Z[i + j * ld];
+        }
+        C* gw = reinterpret_cast<C*>(p.w) + b * (long long)n;
+        for (int e = tid; e < n; e += NT) {
+            if constexpr (CPLX) gw[e] = S.H[e + e * ld];
+            else gw[e] = S.sW[e];
+        }
+        if (tid == 0) {
+            if (p.info) p.info[b] = info;
+            if (p.stats) {
+                p.stats[4 * b + 0] = s_stats[0];
+                p.stats[4 * b + 1] = s_stats[1];
+                p.stats[4 * b + 2] = s_stats[2];
+                p.stats[4 * b + 3] = s_stats[3];
+            }
+        }
+        __syncthreads();
+    }
+}
+
+template <class T, int CPL> int launch_fast(const BatchedParams& p, int dev_sms, cudaStream_t stream, std::string* err) {
+    auto kern = gschur_fast_kernel<T, CPL>;
+    size_t smem = fast_smem_layout<T>::bytes(p.n);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 64, smem);
+    if (e != cudaSuccess) {
+        *err = std::string("kernel setup: ") + cudaGetErrorString(e);
+        return -2;
+    }
+    if (per_sm < 1) {
+        *err = "kernel does not fit on an SM";
+        return -3;
+    }
+    long long grid = (long long)per_sm * dev_sms;
+    if (grid > p.batch) grid = p.batch;
+    kern<<<(unsigned)grid, 64, smem, stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        *err = std::string("kernel launch: ") + cudaGetErrorString(e);
+        return -2;
+    }
+    return 0;
+}
+
+}  // namespace gs

@@ -160,6 +160,42 @@ template <class R> GS_DEV R r_hypot(const R& a, const R& b) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Fast Float64 primitives for the reflector on the serial critical path of the QR sweeps.
+// IEEE division / sqrt cost ~25-30 dependent instructions each (with slow-path branches); the
+// reflector needs one sqrt and two reciprocals per bulge step.  Operands are first scaled by an exact
+// power of two so that they are O(1); then MUFU seeds + Newton steps give results within ~1 ulp with
+// no special-case branches.
+// ------------------------------------------------------------------------------------------------
+GS_DEV double fast_rcp(double a) {   // a finite, normal, non-zero
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+GS_DEV double fast_sqrt(double a) {  // a in a safe range (no denormals / overflow in a*y)
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    // y <- y (1 + e/2 + 3 e^2 / 8),  e = 1 - a y^2   (one cubic step: 20 -> 60+ bits)
+    double ay = a * y;
+    double e = fma(-ay, y, 1.0);
+    double c = fma(e, 0.375, 0.5);
+    y = fma(y * e, c, y);
+    double s = a * y;                 // sqrt(a) ~ a * rsqrt(a), then one correction
+    double r = fma(-s, s, a);
+    return fma(0.5 * y, r, s);
+}
+// exact powers of two 2^-e and 2^e with e = exponent(w); w finite and > 0 (subnormal w: e = -1022)
+GS_DEV void pow2_scales(double w, double& down, double& up) {
+    int ex = (__double2hiint(w) >> 20) & 0x7ff;      // biased exponent
+    ex = ex < 1 ? 1 : (ex > 2045 ? 2045 : ex);
+    down = __hiloint2double((2046 - ex) << 20, 0);   // 2^(1023 - ex)
+    up = __hiloint2double(ex << 20, 0);              // 2^(ex - 1023)
+}
+
+// ------------------------------------------------------------------------------------------------
 // complex
 // ------------------------------------------------------------------------------------------------
 template <class R> struct __align__(16) cx {

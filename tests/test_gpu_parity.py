@@ -18,14 +18,34 @@ from common import ULP, csort, fnorm, godunov, match_eigs, reference_classes, st
 pytestmark = pytest.mark.gpu
 
 
+WELL_CONDITIONED = 1e-6     # first-order eigenvalue bounds are only trusted for s_i above this
+
+
 def _eig_tol(O, A):
+    """(scale, oracle eigenvalues of A/scale, per-eigenvalue tolerance 1e3 ulp ||A|| / s_i).  For (nearly) defective
+    eigenvalues (s_i < 1e-6: Jordan blocks, the latme classes with similarity condition 1/sqrt(ulp) and eigenvalue
+    condition 1/ulp) the first-order bound does not hold — the reference's authors say as much at
+    test/complex.jl:22-25 — and the tolerance is left open; those are covered by the sigma_min check below."""
     sc = float(np.max(np.abs(A))) or 1.0
     Ac = np.asfortranarray((A / sc).astype(np.complex128))
     Tc, _, wc, rc, _ = O.gschur(Ac, 1)
     assert rc == 0
     s = O.eigvalscond(Tc, 1)
-    s = np.where(np.isfinite(s) & (s > 0), s, 1e-300)
-    return sc, wc, 1e3 * ULP * fnorm(Ac) / s
+    ok = np.isfinite(s) & (s >= WELL_CONDITIONED)
+    tol = np.where(ok, 1e3 * ULP * fnorm(Ac) / np.where(ok, s, 1.0), np.inf)
+    return sc, wc, tol
+
+
+def _sigma_min_check(A, w, name, c=100.0):
+    """Every computed eigenvalue is an exact eigenvalue of a matrix within c n ulp ||A|| of A:
+    sigma_min(A - lambda I) <= c n ulp ||A||_F.  Ordering-free and valid for any conditioning."""
+    sc = float(np.max(np.abs(A))) or 1.0
+    As = np.asarray(A, dtype=np.complex128) / sc
+    n = As.shape[0]
+    bound = c * n * ULP * max(fnorm(As), np.finfo(float).tiny)
+    for lam in np.asarray(w) / sc:
+        smin = np.linalg.svd(As - lam * np.eye(n), compute_uv=False)[-1]
+        assert smin <= bound, (name, lam, smin / bound)
 
 
 def _check_one(O, A, T, Z, w, kind, tol, name):
@@ -33,8 +53,9 @@ def _check_one(O, A, T, Z, w, kind, tol, name):
     assert ok, (name, why)
     berr, oerr, _ = O.residuals(A, T, Z, kind)
     assert berr < tol and oerr < tol, (name, berr, oerr)
+    _sigma_min_check(A, w, name)
     sc, wc, etol = _eig_tol(O, A)
-    d = match_eigs(w / sc, wc, etol)
+    d = match_eigs(w / sc, wc, np.where(np.isfinite(etol), etol, 1e300))
     assert np.all(d <= etol), (name, float(np.max(d / etol)))
 
 
@@ -61,11 +82,12 @@ def test_golden_fixtures(gs, O, golden):
         assert S.info == 0, key
         berr, oerr, _ = O.residuals(A, S.T, S.Z, kind)
         assert berr < tol and oerr < tol, (key, berr, oerr)
+        _sigma_min_check(A, S.values, key)
         sc, wc, etol = _eig_tol(O, A)
         for ref in (golden[key + "__w"], golden[key + "__wlapack"]):
             if np.any(np.isnan(ref)):
                 continue
-            d = match_eigs(S.values / sc, ref / sc, etol)
+            d = match_eigs(S.values / sc, ref / sc, np.where(np.isfinite(etol), etol, 1e300))
             assert np.all(d <= 2 * etol), (key, float(np.max(d / etol)))
 
 
