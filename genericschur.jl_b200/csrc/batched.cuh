@@ -1145,6 +1145,7 @@ template <class T, int NT> int launch_nt(const BatchedParams& p, int dev_sms, cu
     long long grid = (long long)per_sm * dev_sms;
     if (grid > p.batch) grid = p.batch;
     kern<<<(unsigned)grid, NT, smem, stream>>>(p);
+    note_launch();
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         *err = std::string("kernel launch: ") + cudaGetErrorString(e);

@@ -14,10 +14,17 @@
 //     carry registers as well (one load + one store per row and step).  It never blocks the H-warp unless it
 //     falls two sweeps behind.
 //
+// Storage.  The Hessenberg matrix is kept in PACKED form in shared memory — column j holds rows 1..j+EX, EX = 2
+// (complex: one bulge entry below the sub-diagonal) or 3 (real double shift: two) — which halves its footprint
+// (64x64 ComplexF64: 35 KB instead of 65 KB).  Z is NOT kept on chip: nothing on the critical path ever reads it, so
+// the Z-warp streams it through L2 (one coalesced column load and store per reflector, software-prefetched) in
+// place in the caller's Z buffer.  Together that is ~45 KB of shared memory per matrix instead of 142 KB, i.e. five
+// CTAs per SM instead of one — occupancy is what this latency-bound algorithm needs.
+//
 // The arithmetic per reflector application and every decision rule are those of batched.cuh (and of the
-// reference, src/GenericSchur.jl:194-335, 374-504, 513-699, 837-952); only the schedule differs.
+// reference, src/GenericSchur.jl:194-335, 374-504, 513-699, 837-952); only the schedule and the layout differ.
 #pragma once
-#include "batched.cuh"
+#include "gehrd.cuh"
 
 namespace gs {
 
@@ -59,26 +66,104 @@ GS_DEV void named_bar_arrive(int id, int) {
     }
 }
 
+// typed shared-memory access through 32-bit shared-space byte addresses (no generic->shared conversion and no
+// 64-bit address arithmetic inside the step loops)
+template <class T> GS_DEV T lds_e(uint32_t a);
+template <> GS_DEV double lds_e<double>(uint32_t a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+template <> GS_DEV cx<double> lds_e<cx<double>>(uint32_t a) {
+    cx<double> v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.re), "=d"(v.im) : "r"(a));
+    return v;
+}
+template <class T> GS_DEV void sts_e(uint32_t a, const T& v);
+template <> GS_DEV void sts_e<double>(uint32_t a, const double& v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+template <> GS_DEV void sts_e<cx<double>>(uint32_t a, const cx<double>& v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.re), "d"(v.im) : "memory");
+}
+
 template <class T, int CPL> struct FastSolver {
     typedef typename etraits<T>::real R;
     typedef cx<R> C;
     static constexpr bool CPLX = etraits<T>::is_complex;
     typedef zop_t<CPLX> ZOp;
 
-    int n, ld, lane, cap;
-    T* H;
-    T* Z;
+    static constexpr int EX = CPLX ? 2 : 3;   // rows stored below the diagonal in each packed column
+    int n, ldz, lane, cap;
+    T* H;            // packed upper Hessenberg (+ bulge slots), shared memory
+    T* Z;            // Schur vectors, global memory (column-major, leading dimension ldz)
     C* sW;
     ZOp* ring;        // [2][cap]
     zring_hdr* hdr;
     bool wantZ;
     unsigned* stp;
-    BatchedSolver<T, 32> B;   // shared decision rules (split tests, first column), run by the H-warp alone
     // producer state (uniform across the H-warp)
     int sidx, cnt;
 
-#define HH(i, j) H[((i)-1) + ((j)-1) * ld]
-#define ZZ(i, j) Z[((i)-1) + ((j)-1) * ld]
+    __host__ __device__ static int colbase(int j) { return ((j - 1) * (j + 2 * EX)) / 2; }   // offset of column j
+    __host__ __device__ static int packed_elems(int n) { return (n * (n + 1)) / 2 + EX * n; }
+#define HH(i, j) H[colbase(j) + (i)-1]
+#define ZZ(i, j) Z[((i)-1) + (size_t)((j)-1) * ldz]
+
+    // ---- decision rules (same as BatchedSolver::split_test_c / split_test_r / first_column_r, packed accessor) ----
+    GS_DEV bool split_test_c(int c, const R& smallnum, const R& ulp) {
+        const R zero = r_const<R>(0.0);
+        C h10 = HH(c + 1, c);
+        if (abs1(h10) <= smallnum) return true;
+        C hcc = HH(c, c), hc1 = HH(c + 1, c + 1);
+        R tst = abs1(hcc) + abs1(hc1);
+        if (tst == zero) {
+            if (c - 1 >= 1) tst = tst + r_abs(HH(c, c - 1).re);
+            if (c + 2 <= n) tst = tst + r_abs(HH(c + 2, c + 1).re);
+        }
+        if (r_abs(h10.re) <= ulp * tst) {
+            R a1 = abs1(h10), a2 = abs1(HH(c, c + 1));
+            R ab = r_max(a1, a2), ba = r_min(a1, a2);
+            R d1 = abs1(hc1), d2 = abs1(hcc - hc1);
+            R aa = r_max(d1, d2), bb = r_min(d1, d2);
+            R s = aa + ab;
+            if (ba * (ab / s) <= r_max(smallnum, ulp * (bb * (aa / s)))) return true;
+        }
+        return false;
+    }
+    GS_DEV bool split_test_r(int k, const R& smallnum, const R& eps) {
+        const R zero = r_const<R>(0.0);
+        R h = r_abs(HH(k, k - 1));
+        if (h < smallnum) return true;
+        R Hkk = HH(k, k), Hk1 = HH(k - 1, k - 1);
+        R t = r_abs(Hk1) + r_abs(Hkk);
+        if (t == zero) {
+            if (k > 2) t = t + r_abs(HH(k - 1, k - 2));
+            if (k + 1 <= n) t = t + r_abs(HH(k + 1, k));
+        }
+        if (h <= t * eps) {
+            R o = r_abs(HH(k - 1, k));
+            R ab = r_max(h, o), ba = r_min(h, o);
+            R d1 = r_abs(Hkk), d2 = r_abs(Hk1 - Hkk);
+            R aa = r_max(d1, d2), bb = r_min(d1, d2);
+            R s = aa + bb;   // as the reference has it (src/GenericSchur.jl:586)
+            if (ba * (ab / s) <= r_max(smallnum, eps * (bb * (aa / s)))) return true;
+        }
+        return false;
+    }
+    GS_DEV void first_column_r(int m, const R& r1r, const R& r1i, const R& r2r, const R& r2i, R& v0, R& v1, R& v2) {
+        R hmm = HH(m, m);
+        R H21s = HH(m + 1, m);
+        R s = r_abs(hmm - r2r) + r_abs(r2i) + r_abs(H21s);
+        H21s = H21s / s;
+        v0 = H21s * HH(m, m + 1) + (hmm - r1r) * ((hmm - r2r) / s) - r1i * (r2i / s);
+        v1 = H21s * (hmm + HH(m + 1, m + 1) - r1r - r2r);
+        v2 = H21s * HH(m + 2, m + 1);
+        s = r_abs(v0) + r_abs(v1) + r_abs(v2);
+        v0 = v0 / s;
+        v1 = v1 / s;
+        v2 = v2 / s;
+    }
 
     // ------------------------------------------------------------------------------------------------
     // producer side of the Z ring
@@ -107,6 +192,28 @@ template <class T, int CPL> struct FastSolver {
         }
     }
     GS_DEV ZOp* slot() { return ring + (sidx & 1) * cap + cnt; }
+    // make room for m ops once, so that the step loop can push without checking
+    GS_DEV void reserve_ops(int m) { ensure_space(m < cap ? m : cap); }
+    GS_DEV void push_refl_c(int k, const C& tau1, const C& v2) {
+        if (!wantZ) return;
+        if (lane == 0) {
+            const uint32_t a = smem_u32(ring + (sidx & 1) * cap + cnt);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"((int)ZOP_REFL), "r"(k) : "memory");
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 16), "d"(tau1.re), "d"(tau1.im) : "memory");
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 32), "d"(v2.re), "d"(v2.im) : "memory");
+        }
+        cnt += 1;
+    }
+    GS_DEV void push_r(int op, int k, double a0, double a1, double a2) {
+        if (!wantZ) return;
+        if (lane == 0) {
+            const uint32_t a = smem_u32(ring + (sidx & 1) * cap + cnt);
+            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(op), "r"(k) : "memory");
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(a + 8), "d"(a0) : "memory");
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 16), "d"(a1), "d"(a2) : "memory");
+        }
+        cnt += 1;
+    }
     GS_DEV void finish_ring() {
         if (!wantZ) return;
         publish(1);
@@ -179,34 +286,50 @@ template <class T, int CPL> struct FastSolver {
             v0 = mk_cx<R>(h11s.re / s, h11s.im / s);
             v1 = mk_cx<R>(h21 / s, zero);
         }
-        // carries: cL[s] = H[k, j] for the owned column j >= k;  dR[s] = H[i, k] for the owned row i < k
-        C cL[CPL], dR[CPL];
+        reserve_ops(iend - k0 + 4);
+        // All shared-memory traffic of the step loop goes through 32-bit byte addresses:
+        //   &H(i, j) = hb + ES * (colbase(j) - 1 + i).   jj / ii are the owned column / row (sentinels when > n).
+        constexpr uint32_t ES = (uint32_t)sizeof(T);
+        const uint32_t hb = smem_u32(H);
+        uint32_t ca[CPL], ib[CPL];
+        int jj[CPL], ii[CPL];
+        C cL[CPL], dR[CPL];   // cL = H[k, j] for the owned column j >= k;  dR = H[i, k] for the owned row i < k
+        uint32_t ak = hb + ES * (uint32_t)(colbase(k0) - 1);   // column k
 #pragma unroll
         for (int s = 0; s < CPL; ++s) {
             const int j = lane + 1 + 32 * s;
-            cL[s] = (j >= k0 && j <= n) ? HH(k0, j) : mk_cx<R>(zero, zero);
-            dR[s] = (j < k0) ? HH(j, k0) : mk_cx<R>(zero, zero);
+            const bool valid = j <= n;
+            jj[s] = valid ? j : -(1 << 28);
+            ii[s] = valid ? j : (1 << 28);
+            ca[s] = hb + ES * (uint32_t)(colbase(valid ? j : 1) - 1);
+            ib[s] = ES * (uint32_t)(valid ? j : 1);
+            cL[s] = (jj[s] >= k0) ? lds_e<T>(ca[s] + ES * k0) : mk_cx<R>(zero, zero);
+            dR[s] = (ii[s] < k0) ? lds_e<T>(ak + ib[s]) : mk_cx<R>(zero, zero);
         }
+        unsigned napplied = 0;
         for (int k = k0; k <= iend - 1; ++k) {
+            const uint32_t kb = ES * (uint32_t)k;
+            const uint32_t ak1 = ak + ES * (uint32_t)(k + EX);          // column k+1
+            const uint32_t akm = ak - ES * (uint32_t)(k - 1 + EX);      // column k-1
             if (k > k0) {
-                v0 = HH(k, k - 1);
-                v1 = HH(k + 1, k - 1);
+                v0 = lds_e<T>(akm + kb);
+                v1 = lds_e<T>(akm + kb + ES);
             }
             const C tau1 = reflector_cplx2(v0, v1);
-            stp[1] += 1;
+            napplied += 1;
             const C v2 = v1, v2c = cconj(v1), tau1c = cconj(tau1);
             const R tau2 = (tau1 * v2).re;
-            emit_refl_c(k, tau1, v2);
+            push_refl_c(k, tau1, v2);
             // ---- left update of rows k, k+1: owned columns j >= k ----
 #pragma unroll
             for (int s = 0; s < CPL; ++s) {
-                const int j = lane + 1 + 32 * s;
-                if (j >= k && j <= n) {
-                    const C b = HH(k + 1, j);
+                if (jj[s] >= k) {
+                    const uint32_t a = ca[s] + kb;
+                    const C b = lds_e<T>(a + ES);
                     const C ss = tau1c * cL[s] + tau2 * b;
-                    HH(k, j) = cL[s] - ss;
+                    sts_e<T>(a, cL[s] - ss);
                     cL[s] = b - ss * v2;
-                    if (j <= k + 1) HH(k + 1, j) = cL[s];   // diagonal columns publish their carry
+                    if (jj[s] <= k + 1) sts_e<T>(a + ES, cL[s]);   // diagonal columns publish their carry
                 }
             }
             __syncwarp();
@@ -214,25 +337,25 @@ template <class T, int CPL> struct FastSolver {
             const int jmax = (k + 2 < iend) ? k + 2 : iend;
 #pragma unroll
             for (int s = 0; s < CPL; ++s) {
-                const int i = lane + 1 + 32 * s;
-                if (i <= jmax) {
-                    const C d = (i >= k) ? HH(i, k) : dR[s];
-                    const C e = HH(i, k + 1);
+                if (ii[s] <= jmax) {
+                    const C d = (ii[s] >= k) ? lds_e<T>(ak + ib[s]) : dR[s];
+                    const C e = lds_e<T>(ak1 + ib[s]);
                     const C ss = tau1 * d + tau2 * e;
-                    HH(i, k) = d - ss;
+                    sts_e<T>(ak + ib[s], d - ss);
                     dR[s] = e - ss * v2c;
-                    if (i >= k + 1) HH(i, k + 1) = dR[s];
+                    if (ii[s] >= k + 1) sts_e<T>(ak1 + ib[s], dR[s]);
                 }
             }
             if (lane == 0 && k > k0) {
-                HH(k, k - 1) = v0;
-                HH(k + 1, k - 1) = mk_cx<R>(zero, zero);
+                sts_e<T>(akm + kb, v0);
+                sts_e<T>(akm + kb + ES, mk_cx<R>(zero, zero));
             }
             __syncwarp();
             // column k+1's running entry H[k+1,k+1] was just rewritten by its own lane as row k+1
 #pragma unroll
             for (int s = 0; s < CPL; ++s)
-                if (lane + 1 + 32 * s == k + 1) cL[s] = dR[s];
+                if (jj[s] == k + 1) cL[s] = dR[s];
+            ak = ak1;
 
             if (k == k0 && k0 > istart) {
                 // late start (src/GenericSchur.jl:461-482): flush the carries, rescale in shared memory, reload
@@ -268,6 +391,7 @@ template <class T, int CPL> struct FastSolver {
                 }
             }
         }
+        stp[1] += napplied;
         // ---- flush the carries left after the last step (k = iend-1) ----
 #pragma unroll
         for (int s = 0; s < CPL; ++s) {
@@ -313,7 +437,7 @@ template <class T, int CPL> struct FastSolver {
                 int found = 0;
                 for (int base = iend - 1; base >= istart && !found; base -= 32) {
                     int c = base - lane;
-                    bool hit = (c >= istart) ? B.split_test_c(c, smallnum, ulp) : false;
+                    bool hit = (c >= istart) ? split_test_c(c, smallnum, ulp) : false;
                     unsigned m = __ballot_sync(0xffffffffu, hit);
                     if (m) found = base - (__ffs(m) - 1);
                 }
@@ -390,7 +514,7 @@ template <class T, int CPL> struct FastSolver {
             bool hit = false;
             if (m >= istart + 1) {
                 R a0, a1, a2;
-                B.first_column_r(m, r1r, r1i, r2r, r2i, a0, a1, a2);
+                first_column_r(m, r1r, r1i, r2r, r2i, a0, a1, a2);
                 hit = r_abs(HH(m, m - 1)) * (r_abs(a1) + r_abs(a2)) <=
                       eps * r_abs(a0) * (r_abs(HH(m - 1, m - 1)) + r_abs(HH(m, m)) + r_abs(HH(m + 1, m + 1)));
             }
@@ -399,41 +523,61 @@ template <class T, int CPL> struct FastSolver {
         }
         if (!mx) mx = istart;
         R v0, v1, v2;
-        B.first_column_r(mx, r1r, r1i, r2r, r2i, v0, v1, v2);
+        first_column_r(mx, r1r, r1i, r2r, r2i, v0, v1, v2);
+        reserve_ops(iend - mx + 4);
+        // byte-address arithmetic as in sweep_complex: &H(i, j) = hb + ES * (colbase(j) - 1 + i)
+        constexpr uint32_t ES = (uint32_t)sizeof(T);
+        const uint32_t hb = smem_u32(H);
+        uint32_t ca[CPL], ib[CPL];
+        int jj[CPL], ii[CPL];
         // carries: (cL1, cL2) = H[k, j], H[k+1, j] for owned columns j >= k;  (dR1, dR2) = H[i, k], H[i, k+1], rows i < k
         R cL1[CPL], cL2[CPL], dR1[CPL], dR2[CPL];
-#pragma unroll
-        for (int s = 0; s < CPL; ++s) {
-            const int j = lane + 1 + 32 * s;
-            const bool c = (j >= mx && j <= n), r = (j < mx);
-            cL1[s] = c ? HH(mx, j) : zero;
-            cL2[s] = c ? HH(mx + 1, j) : zero;
-            dR1[s] = r ? HH(j, mx) : zero;
-            dR2[s] = r ? HH(j, mx + 1) : zero;
-        }
-        int k = mx;
-        for (; k <= iend - 2; ++k) {   // three-row reflectors
-            if (k > mx) {
-                v0 = HH(k, k - 1);
-                v1 = HH(k + 1, k - 1);
-                v2 = HH(k + 2, k - 1);
-            }
-            const R tau1 = reflector_real_small(v0, v1, v2, 3);
-            stp[1] += 1;
-            const R tau2 = tau1 * v1, tau3 = tau1 * v2;
-            emit_r(ZOP_REFL3, k, tau1, v1, v2);
+        uint32_t ak = hb + ES * (uint32_t)(colbase(mx) - 1);
+        {
+            const uint32_t ak1 = ak + ES * (uint32_t)(mx + EX);
 #pragma unroll
             for (int s = 0; s < CPL; ++s) {
                 const int j = lane + 1 + 32 * s;
-                if (j >= k && j <= n) {
-                    const R b = HH(k + 2, j);
+                const bool valid = j <= n;
+                jj[s] = valid ? j : -(1 << 28);
+                ii[s] = valid ? j : (1 << 28);
+                ca[s] = hb + ES * (uint32_t)(colbase(valid ? j : 1) - 1);
+                ib[s] = ES * (uint32_t)(valid ? j : 1);
+                const bool c = jj[s] >= mx, r = ii[s] < mx;
+                cL1[s] = c ? lds_e<T>(ca[s] + ES * mx) : zero;
+                cL2[s] = c ? lds_e<T>(ca[s] + ES * (mx + 1)) : zero;
+                dR1[s] = r ? lds_e<T>(ak + ib[s]) : zero;
+                dR2[s] = r ? lds_e<T>(ak1 + ib[s]) : zero;
+            }
+        }
+        unsigned napplied = 0;
+        int k = mx;
+        for (; k <= iend - 2; ++k) {   // three-row reflectors
+            const uint32_t kb = ES * (uint32_t)k;
+            const uint32_t ak1 = ak + ES * (uint32_t)(k + EX);          // column k+1
+            const uint32_t ak2 = ak1 + ES * (uint32_t)(k + 1 + EX);     // column k+2
+            const uint32_t akm = ak - ES * (uint32_t)(k - 1 + EX);      // column k-1
+            if (k > mx) {
+                v0 = lds_e<T>(akm + kb);
+                v1 = lds_e<T>(akm + kb + ES);
+                v2 = lds_e<T>(akm + kb + 2 * ES);
+            }
+            const R tau1 = reflector_real_small(v0, v1, v2, 3);
+            napplied += 1;
+            const R tau2 = tau1 * v1, tau3 = tau1 * v2;
+            push_r(ZOP_REFL3, k, tau1, v1, v2);
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                if (jj[s] >= k) {
+                    const uint32_t a = ca[s] + kb;
+                    const R b = lds_e<T>(a + 2 * ES);
                     const R ss = cL1[s] + v1 * cL2[s] + v2 * b;
-                    HH(k, j) = cL1[s] - ss * tau1;
+                    sts_e<T>(a, cL1[s] - ss * tau1);
                     cL1[s] = cL2[s] - ss * tau2;
                     cL2[s] = b - ss * tau3;
-                    if (j <= k + 2) {
-                        HH(k + 1, j) = cL1[s];
-                        HH(k + 2, j) = cL2[s];
+                    if (jj[s] <= k + 2) {
+                        sts_e<T>(a + ES, cL1[s]);
+                        sts_e<T>(a + 2 * ES, cL2[s]);
                     }
                 }
             }
@@ -441,46 +585,42 @@ template <class T, int CPL> struct FastSolver {
             const int jmax = (k + 3 < iend) ? k + 3 : iend;
 #pragma unroll
             for (int s = 0; s < CPL; ++s) {
-                const int i = lane + 1 + 32 * s;
-                if (i <= jmax) {
-                    R d1, d2;
-                    if (i >= k) {
-                        d1 = HH(i, k);
-                        d2 = HH(i, k + 1);
-                    } else {
-                        d1 = dR1[s];
-                        d2 = dR2[s];
+                if (ii[s] <= jmax) {
+                    R d1 = dR1[s], d2 = dR2[s];
+                    if (ii[s] >= k) {
+                        d1 = lds_e<T>(ak + ib[s]);
+                        d2 = lds_e<T>(ak1 + ib[s]);
                     }
-                    const R e = HH(i, k + 2);
+                    const R e = lds_e<T>(ak2 + ib[s]);
                     const R ss = d1 + v1 * d2 + v2 * e;
-                    HH(i, k) = d1 - ss * tau1;
+                    sts_e<T>(ak + ib[s], d1 - ss * tau1);
                     dR1[s] = d2 - ss * tau2;
                     dR2[s] = e - ss * tau3;
-                    if (i >= k + 1) {
-                        HH(i, k + 1) = dR1[s];
-                        HH(i, k + 2) = dR2[s];
+                    if (ii[s] >= k + 1) {
+                        sts_e<T>(ak1 + ib[s], dR1[s]);
+                        sts_e<T>(ak2 + ib[s], dR2[s]);
                     }
                 }
             }
             if (lane == 0) {
                 if (k > mx) {
-                    HH(k, k - 1) = v0;
-                    HH(k + 1, k - 1) = zero;
-                    HH(k + 2, k - 1) = zero;
+                    sts_e<T>(akm + kb, v0);
+                    sts_e<T>(akm + kb + ES, zero);
+                    sts_e<T>(akm + kb + 2 * ES, zero);
                 } else if (mx > istart) {
-                    HH(k, k - 1) = HH(k, k - 1) * (one - tau1);
+                    sts_e<T>(akm + kb, lds_e<T>(akm + kb) * (one - tau1));
                 }
             }
             __syncwarp();
             // columns k+1, k+2 were rewritten by the right update in rows k+1, k+2: refresh their carries
 #pragma unroll
             for (int s = 0; s < CPL; ++s) {
-                const int j = lane + 1 + 32 * s;
-                if (j == k + 1 || j == k + 2) {
-                    cL1[s] = HH(k + 1, j);
-                    cL2[s] = HH(k + 2, j);
+                if (jj[s] == k + 1 || jj[s] == k + 2) {
+                    cL1[s] = lds_e<T>(ca[s] + kb + ES);
+                    cL2[s] = lds_e<T>(ca[s] + kb + 2 * ES);
                 }
             }
+            ak = ak1;
         }
         // ---- last step: two-row reflector at k = iend-1; everything is written back ----
         {
@@ -488,7 +628,7 @@ template <class T, int CPL> struct FastSolver {
             v1 = HH(k + 1, k - 1);
             v2 = zero;
             const R tau1 = reflector_real_small(v0, v1, v2, 2);
-            stp[1] += 1;
+            napplied += 1;
             const R tau2 = tau1 * v1;
             emit_r(ZOP_REFL2, k, tau1, v1, zero);
 #pragma unroll
@@ -524,7 +664,9 @@ template <class T, int CPL> struct FastSolver {
             }
             __syncwarp();
         }
+        stp[1] += napplied;
     }
+
 
     GS_DEV int qr_real(int maxiter, unsigned* st) {
         stp = st;
@@ -549,7 +691,7 @@ template <class T, int CPL> struct FastSolver {
                 int found = 0;
                 for (int base = iend; base >= istart + 1 && !found; base -= 32) {
                     int k = base - lane;
-                    bool hit = (k >= istart + 1) ? B.split_test_r(k, smallnum, eps) : false;
+                    bool hit = (k >= istart + 1) ? split_test_r(k, smallnum, eps) : false;
                     unsigned m = __ballot_sync(0xffffffffu, hit);
                     if (m) found = base - (__ffs(m) - 1);
                 }
@@ -656,7 +798,8 @@ template <class T, int CPL> struct FastSolver {
     }
 
     // ================================================================================================
-    // consumer: the Z-warp
+    // consumer: the Z-warp.  Z lives in global memory (L2-resident while the matrix is being worked on); lane l owns
+    // rows l+1 (+32 s).  Runs of consecutive reflectors are streamed with carry registers and a one-column prefetch.
     // ================================================================================================
     GS_DEV void z_consumer() {
         const R zero = r_const<R>(0.0);
@@ -672,25 +815,33 @@ template <class T, int CPL> struct FastSolver {
                 if constexpr (CPLX) {
                     if (op == ZOP_REFL) {
                         int k = ops[i].k;
-                        C z0[CPL];
+                        C z0[CPL], zn[CPL];
 #pragma unroll
                         for (int s = 0; s < CPL; ++s) {
                             const int r = lane + 1 + 32 * s;
                             z0[s] = (r <= n) ? ZZ(r, k) : mk_cx<R>(zero, zero);
+                            zn[s] = (r <= n) ? ZZ(r, k + 1) : mk_cx<R>(zero, zero);
                         }
                         while (i < count && ops[i].op == ZOP_REFL && ops[i].k == k) {
                             const C tau1 = mk_cx<R>(ops[i].a[0], ops[i].a[1]);
                             const C v2 = mk_cx<R>(ops[i].a[2], ops[i].a[3]);
                             const C v2c = cconj(v2);
                             const R tau2 = (tau1 * v2).re;
+                            C zp[CPL];   // prefetch of column k+2 for the next reflector of the run
+#pragma unroll
+                            for (int s = 0; s < CPL; ++s) {
+                                const int r = lane + 1 + 32 * s;
+                                zp[s] = (r <= n && k + 2 <= n) ? ZZ(r, k + 2) : mk_cx<R>(zero, zero);
+                            }
 #pragma unroll
                             for (int s = 0; s < CPL; ++s) {
                                 const int r = lane + 1 + 32 * s;
                                 if (r <= n) {
-                                    const C z1 = ZZ(r, k + 1);
+                                    const C z1 = zn[s];
                                     const C ss = tau1 * z0[s] + tau2 * z1;
                                     ZZ(r, k) = z0[s] - ss;
                                     z0[s] = z1 - ss * v2c;
+                                    zn[s] = zp[s];
                                 }
                             }
                             k += 1;
@@ -715,25 +866,33 @@ template <class T, int CPL> struct FastSolver {
                 } else {
                     if (op == ZOP_REFL3) {
                         int k = ops[i].k;
-                        R z1[CPL], z2[CPL];
+                        R z1[CPL], z2[CPL], zn[CPL];
 #pragma unroll
                         for (int s = 0; s < CPL; ++s) {
                             const int r = lane + 1 + 32 * s;
                             z1[s] = (r <= n) ? ZZ(r, k) : zero;
                             z2[s] = (r <= n) ? ZZ(r, k + 1) : zero;
+                            zn[s] = (r <= n) ? ZZ(r, k + 2) : zero;
                         }
                         while (i < count && ops[i].op == ZOP_REFL3 && ops[i].k == k) {
                             const R tau1 = ops[i].a[0], v2 = ops[i].a[1], v3 = ops[i].a[2];
                             const R tau2 = tau1 * v2, tau3 = tau1 * v3;
+                            R zp[CPL];
+#pragma unroll
+                            for (int s = 0; s < CPL; ++s) {
+                                const int r = lane + 1 + 32 * s;
+                                zp[s] = (r <= n && k + 3 <= n) ? ZZ(r, k + 3) : zero;
+                            }
 #pragma unroll
                             for (int s = 0; s < CPL; ++s) {
                                 const int r = lane + 1 + 32 * s;
                                 if (r <= n) {
-                                    const R z3 = ZZ(r, k + 2);
+                                    const R z3 = zn[s];
                                     const R ss = z1[s] + v2 * z2[s] + v3 * z3;
                                     ZZ(r, k) = z1[s] - ss * tau1;
                                     z1[s] = z2[s] - ss * tau2;
                                     z2[s] = z3 - ss * tau3;
+                                    zn[s] = zp[s];
                                 }
                             }
                             k += 1;
@@ -787,74 +946,56 @@ template <class T, int CPL> struct FastSolver {
 };
 
 // =================================================================================================
-// kernel: one matrix per 64-thread CTA.  Load / scale / Hessenberg / form-Q / store reuse the block-wide code of
-// batched.cuh (all 64 threads); the QR stage runs warp-specialised.
+// Stage B kernel: QR iteration on an upper Hessenberg matrix.  One matrix per 64-thread CTA (H-warp + Z-warp).
+//   in:  A_b = H_b (upper Hessenberg), Z_b = Q_b (or the caller's Z with GSCHUR_FLAG_HESS_INPUT), scratch (scale info)
+//   out: A_b <- T_b, Z_b <- Z_b * (accumulated reflectors), w, info, stats
 // =================================================================================================
-template <class T> struct fast_smem_layout {
+template <class T, int CPL> struct fast_smem_layout {
+    typedef typename etraits<T>::real R;
     typedef smem_layout<T> L;
+    typedef FastSolver<T, CPL> FS;
     typedef zop_t<etraits<T>::is_complex> ZOp;
     __host__ __device__ static int cap(int n) { return n + 8; }
-    __host__ __device__ static size_t off_ring(int n) { return L::up16(L::off_mbar(n) + 16); }
+    __host__ __device__ static size_t off_w(int n) { return L::up16((size_t)FS::packed_elems(n) * sizeof(T)); }
+    __host__ __device__ static size_t off_ring(int n) { return off_w(n) + L::up16((size_t)n * 2 * sizeof(R)); }
     __host__ __device__ static size_t off_hdr(int n) { return off_ring(n) + L::up16(2 * (size_t)cap(n) * sizeof(ZOp)); }
     __host__ __device__ static size_t bytes(int n) { return off_hdr(n) + L::up16(sizeof(zring_hdr)); }
 };
 
+// register budget: small real tiles are occupancy-bound (cap at 64 registers -> 16 CTAs/SM), the others shared-memory-bound
+template <class T, int CPL> struct qr_min_blocks {
+    static constexpr int value = (!etraits<T>::is_complex && CPL == 1 && sizeof(T) == 8) ? 16 : 1;
+};
+
 template <class T, int CPL>
-__global__ void __launch_bounds__(64) gschur_fast_kernel(BatchedParams p) {
+__global__ void __launch_bounds__(64, qr_min_blocks<T, CPL>::value) gschur_qr_kernel(BatchedParams p) {
     typedef typename etraits<T>::real R;
     typedef cx<R> C;
     constexpr bool CPLX = etraits<T>::is_complex;
     constexpr int NT = 64;
+    typedef FastSolver<T, CPL> FS;
+    typedef fast_smem_layout<T, CPL> FL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = p.n, ld = smem_layout<T>::ld(n);
+    const int n = p.n;
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    typedef smem_layout<T> L;
-    typedef fast_smem_layout<T> FL;
-
-    BatchedSolver<T, NT> S;
-    S.n = n;
-    S.ld = ld;
-    S.tid = tid;
-    S.lane = lane;
-    S.H = reinterpret_cast<T*>(smem_raw);
-    S.Z = reinterpret_cast<T*>(smem_raw + L::off_Z(n));
-    S.sTau = reinterpret_cast<T*>(smem_raw + L::off_tau(n));
-    S.sW = reinterpret_cast<C*>(smem_raw + L::off_w(n));
-    S.sRed = reinterpret_cast<R*>(smem_raw + L::off_red(n));
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L::off_mbar(n));
     __shared__ long long s_next;
     __shared__ int s_info;
     __shared__ unsigned s_stats[4];
-    S.wantZ = (p.Z != nullptr);
+    const bool wantZ = (p.Z != nullptr);
 
-    FastSolver<T, CPL> F;
+    FS F;
     F.n = n;
-    F.ld = ld;
     F.lane = lane;
     F.cap = FL::cap(n);
-    F.H = S.H;
-    F.Z = S.Z;
-    F.sW = S.sW;
-    F.ring = reinterpret_cast<typename FastSolver<T, CPL>::ZOp*>(smem_raw + FL::off_ring(n));
+    F.H = reinterpret_cast<T*>(smem_raw);
+    F.sW = reinterpret_cast<C*>(smem_raw + FL::off_w(n));
+    F.ring = reinterpret_cast<typename FS::ZOp*>(smem_raw + FL::off_ring(n));
     F.hdr = reinterpret_cast<zring_hdr*>(smem_raw + FL::off_hdr(n));
-    F.wantZ = S.wantZ;
-    F.B.n = n;
-    F.B.ld = ld;
-    F.B.tid = lane;
-    F.B.lane = lane;
-    F.B.H = S.H;
-    F.B.Z = S.Z;
-    F.B.sTau = S.sTau;
-    F.B.sW = S.sW;
-    F.B.sRed = S.sRed;
-    F.B.wantZ = S.wantZ;
-
-    if (tid == 0) mbar_init(mbar, 1);
-    __syncthreads();
-    uint32_t parity = 0;
-    const size_t mat_bytes = (size_t)n * n * sizeof(T);
-    const bool dense = (p.lda == n);
+    F.wantZ = wantZ;
+    F.ldz = p.ldz;
+    T* H = F.H;
+    const R zero = r_const<R>(0.0);
 
     for (;;) {
         if (tid == 0) s_next = (long long)atomicAdd(p.counter, 1ULL);
@@ -862,58 +1003,26 @@ __global__ void __launch_bounds__(64) gschur_fast_kernel(BatchedParams p) {
         const long long b = s_next;
         __syncthreads();
         if (b >= p.batch) break;
-
         T* gA = reinterpret_cast<T*>(p.A) + b * p.strideA;
-        T* gZ = S.wantZ ? reinterpret_cast<T*>(p.Z) + b * p.strideZ : nullptr;
-        const R zero = r_const<R>(0.0);
+        F.Z = wantZ ? reinterpret_cast<T*>(p.Z) + b * p.strideZ : nullptr;
 
-        const bool use_tma = dense && (mat_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(gA) & 15) == 0);
-        if (use_tma) {
-            if (tid == 0) {
-                fence_proxy_async();
-                mbar_expect_tx(mbar, (uint32_t)mat_bytes);
-                tma_bulk_g2s(S.Z, gA, (uint32_t)mat_bytes, mbar);
-            }
-            mbar_wait(mbar, parity);
-            parity ^= 1;
-            for (int e = tid; e < n * n; e += NT) {
-                int i = e % n, j = e / n;
-                S.H[i + j * ld] = S.Z[e];
-            }
-        } else {
-            for (int e = tid; e < n * n; e += NT) {
-                int i = e % n, j = e / n;
-                S.H[i + j * ld] = gA[i + (size_t)j * p.lda];
-            }
-        }
-        __syncthreads();
-
-        int info = 0;
-        bool scaled = false;
-        R cscale = r_const<R>(1.0), anrm = r_const<R>(1.0);
-        if (p.flags & F_HESS_INPUT) {
-            if (S.wantZ)
-                for (int e = tid; e < n * n; e += NT) {
-                    int i = e % n, j = e / n;
-                    S.Z[i + j * ld] = gZ[i + (size_t)j * p.ldz];
-                }
-            if (CPLX && (p.flags & F_CHECK_SUBDIAG)) {
-                int bad = 0;
+        // ---- load the Hessenberg part into packed storage; bulge slots start at zero ----
+        int bad = 0;
+        for (int j = 1 + warp; j <= n; j += 2) {
+            const int cb = FS::colbase(j);
+            for (int i = 1 + lane; i <= j + FS::EX; i += 32) {
+                T v = e_zero<T>();
+                if (i <= j + 1 && i <= n) v = gA[(i - 1) + (size_t)(j - 1) * p.lda];
+                H[cb + i - 1] = v;
                 if constexpr (CPLX) {
-                    for (int j = 1 + tid; j <= n - 1; j += NT)
-                        if (S.H[j + (j - 1) * ld].im != zero) bad = 1;
+                    if (i == j + 1 && (p.flags & F_CHECK_SUBDIAG) && v.im != zero) bad = 1;
                 }
-                bad = __syncthreads_or(bad);
-                if (bad) info = -4;
             }
-            __syncthreads();
-        } else {
-            if (p.scale) scaled = S.scale_in(cscale, anrm);
-            S.hessenberg();
-            if (S.wantZ) S.form_q();
         }
+        bad = __syncthreads_or(bad);
+        int info = 0;
+        if (bad) info = -4;
         if (info == 0) {
-            S.zero_below_subdiag();
             const int maxiter = p.maxiter > 0 ? p.maxiter : 100 * n;
             if (warp == 0) {
                 unsigned st[4] = {0u, 0u, 0u, 0u};
@@ -927,7 +1036,7 @@ __global__ void __launch_bounds__(64) gschur_fast_kernel(BatchedParams p) {
                     s_stats[2] = st[2];
                     s_stats[3] = st[3];
                 }
-            } else if (S.wantZ) {
+            } else if (wantZ) {
                 F.z_consumer();
             }
             __syncthreads();
@@ -937,28 +1046,41 @@ __global__ void __launch_bounds__(64) gschur_fast_kernel(BatchedParams p) {
         }
         __syncthreads();
 
+        // ---- unscale (src/GenericSchur.jl:367-370, 830-833) with the factors stage A recorded ----
+        bool scaled = false;
+        R cscale = r_const<R>(1.0), anrm = r_const<R>(1.0);
+        if (p.scratch) {
+            const double* sc = p.scratch + 8 * b;
+            scaled = sc[0] != 0.0;
+            if constexpr (rtraits<R>::ndoubles == 1) {
+                cscale = sc[1];
+                anrm = sc[3];
+            } else {
+                cscale = mk_dd(sc[1], sc[2]);
+                anrm = mk_dd(sc[3], sc[4]);
+            }
+        }
         if (scaled) {
+            const int total = FS::packed_elems(n);
             safescale_apply<T, R, NT>(cscale, anrm, [&](R mul) {
-                for (int e = tid; e < n * n; e += NT) {
-                    int i = e % n, j = e / n;
-                    S.H[i + j * ld] = e_scale(S.H[i + j * ld], mul);
-                }
+                for (int e = tid; e < total; e += NT) H[e] = e_scale(H[e], mul);
                 if (!CPLX)
-                    for (int e = tid; e < n; e += NT) S.sW[e] = mk_cx<R>(S.sW[e].re * mul, S.sW[e].im * mul);
+                    for (int e = tid; e < n; e += NT) F.sW[e] = mk_cx<R>(F.sW[e].re * mul, F.sW[e].im * mul);
             });
             __syncthreads();
         }
-        for (int e = tid; e < n * n; e += NT) {
-            int i = e % n, j = e / n;
-            T v = S.H[i + j * ld];
-            bool keep = CPLX ? (i <= j) : (i <= j + 1);
-            gA[i + (size_t)j * p.lda] = keep ? v : e_zero<T>();
-            if (S.wantZ) gZ[i + (size_t)j * p.ldz] = S.Z[i + j * ld];
+        // ---- store T (exact zeros below the (quasi-)triangle), w, info, stats ----
+        for (int j = 1 + warp; j <= n; j += 2) {
+            const int cb = FS::colbase(j);
+            for (int i = 1 + lane; i <= n; i += 32) {
+                const bool keep = CPLX ? (i <= j) : (i <= j + 1);
+                gA[(i - 1) + (size_t)(j - 1) * p.lda] = keep ? H[cb + i - 1] : e_zero<T>();
+            }
         }
         C* gw = reinterpret_cast<C*>(p.w) + b * (long long)n;
         for (int e = tid; e < n; e += NT) {
-            if constexpr (CPLX) gw[e] = S.H[e + e * ld];
-            else gw[e] = S.sW[e];
+            if constexpr (CPLX) gw[e] = H[FS::colbase(e + 1) + e];
+            else gw[e] = F.sW[e];
         }
         if (tid == 0) {
             if (p.info) p.info[b] = info;
@@ -973,29 +1095,56 @@ __global__ void __launch_bounds__(64) gschur_fast_kernel(BatchedParams p) {
     }
 }
 
-template <class T, int CPL> int launch_fast(const BatchedParams& p, int dev_sms, cudaStream_t stream, std::string* err) {
-    auto kern = gschur_fast_kernel<T, CPL>;
-    size_t smem = fast_smem_layout<T>::bytes(p.n);
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// Two launches on the caller's stream: stage A (unless the input is already Hessenberg), then stage B.
+template <class T, int CPL> int launch_fast(const BatchedParams& p_in, int dev_sms, cudaStream_t stream, std::string* err) {
+    BatchedParams p = p_in;
+    cudaError_t e;
+    double* scratch = nullptr;
+    unsigned long long* counter2 = nullptr;
+    const bool hess_input = (p.flags & F_HESS_INPUT) != 0;
+    if (!hess_input) {
+        e = cudaMallocAsync((void**)&scratch, (size_t)p.batch * 8 * sizeof(double) + 16, stream);
+        if (e != cudaSuccess) {
+            *err = std::string("cudaMallocAsync: ") + cudaGetErrorString(e);
+            return -2;
+        }
+        counter2 = reinterpret_cast<unsigned long long*>(scratch + (size_t)p.batch * 8);
+        e = cudaMemsetAsync(counter2, 0, sizeof(unsigned long long), stream);
+        p.scratch = scratch;
+        int rc = launch_gehrd<T, 64>(p, dev_sms, stream, err);
+        if (rc) {
+            cudaFreeAsync(scratch, stream);
+            return rc;
+        }
+        p.counter = counter2;   // stage B gets its own work-queue head
+    }
+    auto kern = gschur_qr_kernel<T, CPL>;
+    size_t smem = fast_smem_layout<T, CPL>::bytes(p.n);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int per_sm = 0;
     if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 64, smem);
+    int rc = 0;
     if (e != cudaSuccess) {
-        *err = std::string("kernel setup: ") + cudaGetErrorString(e);
-        return -2;
+        *err = std::string("qr kernel setup: ") + cudaGetErrorString(e);
+        rc = -2;
+    } else if (per_sm < 1) {
+        *err = "qr kernel does not fit on an SM";
+        rc = -3;
+    } else {
+        long long grid = (long long)per_sm * dev_sms;
+        if (grid > p.batch) grid = p.batch;
+        kern<<<(unsigned)grid, 64, smem, stream>>>(p);
+        note_launch();
+        e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            *err = std::string("qr kernel launch: ") + cudaGetErrorString(e);
+            rc = -2;
+        }
     }
-    if (per_sm < 1) {
-        *err = "kernel does not fit on an SM";
-        return -3;
-    }
-    long long grid = (long long)per_sm * dev_sms;
-    if (grid > p.batch) grid = p.batch;
-    kern<<<(unsigned)grid, 64, smem, stream>>>(p);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        *err = std::string("kernel launch: ") + cudaGetErrorString(e);
-        return -2;
-    }
-    return 0;
+    if (scratch) cudaFreeAsync(scratch, stream);
+    return rc;
 }
 
 }  // namespace gs

@@ -20,7 +20,6 @@ using namespace gs;
 namespace {
 
 thread_local std::string g_err;
-std::atomic<uint64_t> g_launches{0};
 
 int fail(int code, const std::string& msg) {
     g_err = msg;
@@ -91,7 +90,6 @@ int launch_kind(int kind, const BatchedParams& p, int dev_sms, cudaStream_t stre
         default: return fail(GSCHUR_ERR_ARG, "bad kind");
     }
     if (rc) return fail(rc, err);
-    g_launches.fetch_add(1);
     return 0;
 }
 
@@ -144,6 +142,7 @@ int enqueue_device(int kind, int mode, int n, int64_t batch, void* A, int lda, i
     p.info = info;
     p.stats = stats;
     p.counter = counter;
+    p.scratch = nullptr;
     return launch_kind(kind, p, ds->sm_count, stream);
 }
 
@@ -360,7 +359,7 @@ int gschur_cuda_device_count(void) {
 
 const char* gschur_cuda_last_error(void) { return g_err.c_str(); }
 
-uint64_t gschur_cuda_launch_count(void) { return g_launches.load(); }
+uint64_t gschur_cuda_launch_count(void) { return gs::launch_counter(); }
 
 int gschur_cuda_max_batched_n(int kind) { return max_batched_n(kind); }
 

@@ -18,10 +18,15 @@ struct BatchedParams {
     int* info;
     unsigned* stats;
     unsigned long long* counter;
+    double* scratch;   // two-kernel path: 8 doubles per matrix (scaled flag, cscale, anrm) from stage A to stage B
 };
 
 enum { MODE_SCHUR = 0, MODE_HESSENBERG = 1 };
 enum { F_HESS_INPUT = 0x2u, F_CHECK_SUBDIAG = 0x4u };
+
+// every kernel launch of the library is counted (gschur_cuda_launch_count)
+void note_launch();
+unsigned long long launch_counter();
 
 // dynamic shared memory one CTA needs for an n x n matrix of `kind`
 size_t batched_smem_bytes(int kind, int n);
