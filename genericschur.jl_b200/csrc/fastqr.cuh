@@ -30,14 +30,14 @@ namespace gs {
 
 enum { ZOP_REFL = 1, ZOP_SCALE = 2, ZOP_REFL3 = 3, ZOP_REFL2 = 4, ZOP_GIVENS = 5 };
 
-template <bool CPLX> struct zop_t;
-template <> struct __align__(16) zop_t<true> {   // 48 B
+template <bool CPLX, class R> struct zop_t;
+template <class R> struct __align__(16) zop_t<true, R> {    // 16 B + 4 reals
     int op, k, k2, pad;
-    double a[4];   // REFL: tau1.re, tau1.im, v2.re, v2.im ; SCALE: t.re, t.im (columns k..k2)
+    R a[4];   // REFL: tau1.re, tau1.im, v2.re, v2.im ; SCALE: t.re, t.im (columns k..k2)
 };
-template <> struct __align__(16) zop_t<false> {  // 32 B
+template <class R> struct __align__(16) zop_t<false, R> {   // Float64: 32 B
     int op, k;
-    double a[3];   // REFL3: tau1, v2, v3 ; REFL2: tau1, v2 ; GIVENS: cs, sn (columns k, k+1)
+    R a[3];   // REFL3: tau1, v2, v3 ; REFL2: tau1, v2 ; GIVENS: cs, sn (columns k, k+1)
 };
 
 struct zring_hdr {
@@ -79,7 +79,25 @@ template <> GS_DEV cx<double> lds_e<cx<double>>(uint32_t a) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.re), "=d"(v.im) : "r"(a));
     return v;
 }
+template <> GS_DEV dd_t lds_e<dd_t>(uint32_t a) {
+    dd_t v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.hi), "=d"(v.lo) : "r"(a));
+    return v;
+}
+template <> GS_DEV cx<dd_t> lds_e<cx<dd_t>>(uint32_t a) {
+    cx<dd_t> v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.re.hi), "=d"(v.re.lo) : "r"(a));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.im.hi), "=d"(v.im.lo) : "r"(a + 16));
+    return v;
+}
 template <class T> GS_DEV void sts_e(uint32_t a, const T& v);
+template <> GS_DEV void sts_e<dd_t>(uint32_t a, const dd_t& v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.hi), "d"(v.lo) : "memory");
+}
+template <> GS_DEV void sts_e<cx<dd_t>>(uint32_t a, const cx<dd_t>& v) {
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.re.hi), "d"(v.re.lo) : "memory");
+    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 16), "d"(v.im.hi), "d"(v.im.lo) : "memory");
+}
 template <> GS_DEV void sts_e<double>(uint32_t a, const double& v) {
     asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
 }
@@ -91,7 +109,7 @@ template <class T, int CPL> struct FastSolver {
     typedef typename etraits<T>::real R;
     typedef cx<R> C;
     static constexpr bool CPLX = etraits<T>::is_complex;
-    typedef zop_t<CPLX> ZOp;
+    typedef zop_t<CPLX, R> ZOp;
 
     static constexpr int EX = CPLX ? 2 : 3;   // rows stored below the diagonal in each packed column
     int n, ldz, lane, cap;
@@ -197,20 +215,29 @@ template <class T, int CPL> struct FastSolver {
     GS_DEV void push_refl_c(int k, const C& tau1, const C& v2) {
         if (!wantZ) return;
         if (lane == 0) {
-            const uint32_t a = smem_u32(ring + (sidx & 1) * cap + cnt);
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"((int)ZOP_REFL), "r"(k) : "memory");
-            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 16), "d"(tau1.re), "d"(tau1.im) : "memory");
-            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 32), "d"(v2.re), "d"(v2.im) : "memory");
+            ZOp* e = ring + (sidx & 1) * cap + cnt;
+            if constexpr (CPLX) {
+                e->op = ZOP_REFL;
+                e->k = k;
+                e->a[0] = tau1.re;
+                e->a[1] = tau1.im;
+                e->a[2] = v2.re;
+                e->a[3] = v2.im;
+            }
         }
         cnt += 1;
     }
-    GS_DEV void push_r(int op, int k, double a0, double a1, double a2) {
+    GS_DEV void push_r(int op, int k, const R& a0, const R& a1, const R& a2) {
         if (!wantZ) return;
         if (lane == 0) {
-            const uint32_t a = smem_u32(ring + (sidx & 1) * cap + cnt);
-            asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(op), "r"(k) : "memory");
-            asm volatile("st.shared.f64 [%0], %1;" ::"r"(a + 8), "d"(a0) : "memory");
-            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a + 16), "d"(a1), "d"(a2) : "memory");
+            ZOp* e = ring + (sidx & 1) * cap + cnt;
+            if constexpr (!CPLX) {
+                e->op = op;
+                e->k = k;
+                e->a[0] = a0;
+                e->a[1] = a1;
+                e->a[2] = a2;
+            }
         }
         cnt += 1;
     }
@@ -250,8 +277,8 @@ template <class T, int CPL> struct FastSolver {
             e->k2 = j1;
             e->a[0] = t.re;
             e->a[1] = t.im;
-            e->a[2] = 0.0;
-            e->a[3] = 0.0;
+            e->a[2] = r_const<R>(0.0);
+            e->a[3] = r_const<R>(0.0);
         }
         cnt += 1;
     }
@@ -954,7 +981,7 @@ template <class T, int CPL> struct fast_smem_layout {
     typedef typename etraits<T>::real R;
     typedef smem_layout<T> L;
     typedef FastSolver<T, CPL> FS;
-    typedef zop_t<etraits<T>::is_complex> ZOp;
+    typedef zop_t<etraits<T>::is_complex, typename etraits<T>::real> ZOp;
     __host__ __device__ static int cap(int n) { return n + 8; }
     __host__ __device__ static size_t off_w(int n) { return L::up16((size_t)FS::packed_elems(n) * sizeof(T)); }
     __host__ __device__ static size_t off_ring(int n) { return off_w(n) + L::up16((size_t)n * 2 * sizeof(R)); }

@@ -20,15 +20,23 @@ template <class T> struct gehrd_smem_layout {
     __host__ __device__ static size_t off_red(int n) { return off_tau(n) + L::up16((size_t)n * sizeof(T)); }
     __host__ __device__ static size_t off_mbar(int n) { return off_red(n) + L::up16(32 * sizeof(R)); }
     __host__ __device__ static size_t bytes(int n) { return off_mbar(n) + 16; }
+    // global-tile variant: only tau, the reduction scratch and the (unused) mbarrier live in shared memory
+    __host__ __device__ static size_t up16tau(int n) { return L::up16((size_t)n * sizeof(T)); }
+    __host__ __device__ static size_t bytes_gt(int n) { return up16tau(n) + L::up16(32 * sizeof(R)) + 16; }
 };
 
-template <class T, int NT>
+// GT = true: the n x n tile does not fit in shared memory (ComplexF64 n > 118, complex double-double n > 83):
+// the tile lives in global memory instead — in the caller's Z buffer (or in scratch when Z is not wanted), which
+// is where Q has to end up anyway.  Same code, generic addressing; element-per-thread accesses of 16/32-byte
+// elements use whole 32-byte sectors, so the strided (row) accesses cost no extra L2 traffic.
+template <class T, int NT, bool GT>
 __global__ void __launch_bounds__(NT) gehrd_q_kernel(BatchedParams p) {
     typedef typename etraits<T>::real R;
     constexpr bool CPLX = etraits<T>::is_complex;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     typedef gehrd_smem_layout<T> GL;
-    const int n = p.n, ld = smem_layout<T>::ld(n);
+    const int n = p.n;
+    const int ld = GT ? (p.Z ? p.ldz : n) : smem_layout<T>::ld(n);
     const int tid = threadIdx.x;
 
     BatchedSolver<T, NT> S;
@@ -38,14 +46,14 @@ __global__ void __launch_bounds__(NT) gehrd_q_kernel(BatchedParams p) {
     S.lane = tid & 31;
     S.H = reinterpret_cast<T*>(smem_raw);
     S.Z = nullptr;
-    S.sTau = reinterpret_cast<T*>(smem_raw + GL::off_tau(n));
+    S.sTau = reinterpret_cast<T*>(smem_raw + (GT ? 0 : GL::off_tau(n)));
     S.sW = nullptr;
-    S.sRed = reinterpret_cast<R*>(smem_raw + GL::off_red(n));
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + GL::off_mbar(n));
+    S.sRed = reinterpret_cast<R*>(smem_raw + (GT ? GL::up16tau(n) : GL::off_red(n)));
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + (GT ? GL::up16tau(n) + GL::L::up16(32 * sizeof(R)) : GL::off_mbar(n)));
     __shared__ long long s_next;
     const bool wantZ = (p.Z != nullptr);
     T* H = S.H;
-#define AA(i, j) H[((i)-1) + ((j)-1) * ld]
+#define AA(i, j) H[((i)-1) + (size_t)((j)-1) * ld]
 
     if (tid == 0) mbar_init(mbar, 1);
     __syncthreads();
@@ -60,9 +68,14 @@ __global__ void __launch_bounds__(NT) gehrd_q_kernel(BatchedParams p) {
         if (b >= p.batch) break;
         T* gA = reinterpret_cast<T*>(p.A) + b * p.strideA;
         T* gZ = wantZ ? reinterpret_cast<T*>(p.Z) + b * p.strideZ : nullptr;
+        if (GT) {
+            // tile = this matrix's Z buffer (or its slice of the scratch tile array when Z is not wanted)
+            H = wantZ ? gZ : reinterpret_cast<T*>(p.tau) + (size_t)blockIdx.x * n * n;
+            S.H = H;
+        }
 
         // ---- stage the tile ----
-        const bool use_tma = (sizeof(T) % 16 == 0) && ((reinterpret_cast<uintptr_t>(gA) & 15) == 0) &&
+        const bool use_tma = !GT && (sizeof(T) % 16 == 0) && ((reinterpret_cast<uintptr_t>(gA) & 15) == 0) &&
                              (((size_t)p.lda * sizeof(T)) % 16 == 0);
         if (use_tma) {
             if (tid == 0) {
@@ -77,7 +90,7 @@ __global__ void __launch_bounds__(NT) gehrd_q_kernel(BatchedParams p) {
         } else {
             for (int e = tid; e < n * n; e += NT) {
                 int i = e % n, j = e / n;
-                H[i + j * ld] = gA[i + (size_t)j * p.lda];
+                H[i + (size_t)j * ld] = gA[i + (size_t)j * p.lda];
             }
         }
         __syncthreads();
@@ -89,7 +102,7 @@ __global__ void __launch_bounds__(NT) gehrd_q_kernel(BatchedParams p) {
         // ---- H out (upper Hessenberg part, zeros below) ----
         for (int e = tid; e < n * n; e += NT) {
             int i = e % n, j = e / n;
-            gA[i + (size_t)j * p.lda] = (i <= j + 1) ? H[i + j * ld] : e_zero<T>();
+            gA[i + (size_t)j * p.lda] = (i <= j + 1) ? H[i + (size_t)j * ld] : e_zero<T>();
         }
         if (tid == 0 && p.scratch) {
             double* sc = p.scratch + 8 * b;
@@ -135,19 +148,20 @@ __global__ void __launch_bounds__(NT) gehrd_q_kernel(BatchedParams p) {
                 if (tid == 0) AA(i + 1, i + 1) = e_one<T>() - taui;
                 __syncthreads();
             }
-            for (int e = tid; e < n * n; e += NT) {
-                int i = e % n, j = e / n;
-                gZ[i + (size_t)j * p.ldz] = H[i + j * ld];
-            }
+            if (!GT)
+                for (int e = tid; e < n * n; e += NT) {
+                    int i = e % n, j = e / n;
+                    gZ[i + (size_t)j * p.ldz] = H[i + j * ld];
+                }
         }
         __syncthreads();
     }
 #undef AA
 }
 
-template <class T, int NT> int launch_gehrd(const BatchedParams& p, int dev_sms, cudaStream_t stream, std::string* err) {
-    auto kern = gehrd_q_kernel<T, NT>;
-    size_t smem = gehrd_smem_layout<T>::bytes(p.n);
+template <class T, int NT, bool GT> int launch_gehrd_v(const BatchedParams& p, int dev_sms, cudaStream_t stream, std::string* err) {
+    auto kern = gehrd_q_kernel<T, NT, GT>;
+    size_t smem = GT ? gehrd_smem_layout<T>::bytes_gt(p.n) : gehrd_smem_layout<T>::bytes(p.n);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -163,14 +177,30 @@ template <class T, int NT> int launch_gehrd(const BatchedParams& p, int dev_sms,
     }
     long long grid = (long long)per_sm * dev_sms;
     if (grid > p.batch) grid = p.batch;
-    kern<<<(unsigned)grid, NT, smem, stream>>>(p);
+    BatchedParams q = p;
+    T* tiles = nullptr;
+    if (GT && !p.Z) {
+        // no Z buffer to work in: one scratch tile per resident CTA
+        e = cudaMallocAsync((void**)&tiles, (size_t)grid * p.n * p.n * sizeof(T), stream);
+        if (e != cudaSuccess) {
+            *err = std::string("cudaMallocAsync(tiles): ") + cudaGetErrorString(e);
+            return -2;
+        }
+        q.tau = tiles;
+    }
+    kern<<<(unsigned)grid, NT, smem, stream>>>(q);
     note_launch();
     e = cudaGetLastError();
+    if (tiles) cudaFreeAsync(tiles, stream);
     if (e != cudaSuccess) {
         *err = std::string("gehrd kernel launch: ") + cudaGetErrorString(e);
         return -2;
     }
     return 0;
+}
+template <class T, int NT> int launch_gehrd(const BatchedParams& p, int dev_sms, cudaStream_t stream, std::string* err) {
+    if (gehrd_smem_layout<T>::bytes(p.n) <= 232448) return launch_gehrd_v<T, NT, false>(p, dev_sms, stream, err);
+    return launch_gehrd_v<T, NT, true>(p, dev_sms, stream, err);
 }
 
 }  // namespace gs

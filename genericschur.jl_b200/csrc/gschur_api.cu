@@ -42,7 +42,7 @@ int max_batched_n(int kind) {
     if (kind < 0 || kind > 3) return 0;
     if (!cache[kind]) {
         int n = 1;
-        while (gs::batched_smem_bytes(kind, n + 1) <= kMaxSmem) ++n;
+        while (gs::batched_smem_bytes(kind, n + 1) <= kMaxSmem) ++n;   // single-kernel path (Hessenberg-only requests)
         cache[kind] = n;
     }
     return cache[kind];
@@ -93,8 +93,11 @@ int launch_kind(int kind, const BatchedParams& p, int dev_sms, cudaStream_t stre
     return 0;
 }
 
+// two-kernel Schur path: lanes own up to 4 (Float64 kinds) / 3 (double-double kinds) columns
+int max_schur_n(int kind) { return (kind == GSCHUR_F64 || kind == GSCHUR_C64) ? 128 : 96; }
+
 int check_args(int kind, int n, int64_t batch, const void* A, int lda, int64_t strideA, const void* Z, int ldz,
-               int64_t strideZ, const void* w) {
+               int64_t strideZ, const void* w, bool schur_mode = true) {
     if (kind < 0 || kind > 3) return fail(GSCHUR_ERR_ARG, "kind must be 0..3");
     if (n < 0 || batch < 0) return fail(GSCHUR_ERR_ARG, "n and batch must be non-negative");
     if (n == 0 || batch == 0) return 0;
@@ -106,7 +109,7 @@ int check_args(int kind, int n, int64_t batch, const void* A, int lda, int64_t s
         if (batch > 1 && strideZ < (int64_t)ldz * (n - 1) + n) return fail(GSCHUR_ERR_ARG, "strideZ overlaps matrices");
     }
     if (!w) return fail(GSCHUR_ERR_ARG, "w is NULL");
-    if (n > max_batched_n(kind))
+    if (n > (schur_mode ? max_schur_n(kind) : max_batched_n(kind)))
         return fail(GSCHUR_ERR_SIZE, "n = " + std::to_string(n) + " exceeds the batched-kernel limit " +
                                          std::to_string(max_batched_n(kind)) + " for this kind");
     return 0;
@@ -361,7 +364,10 @@ const char* gschur_cuda_last_error(void) { return g_err.c_str(); }
 
 uint64_t gschur_cuda_launch_count(void) { return gs::launch_counter(); }
 
-int gschur_cuda_max_batched_n(int kind) { return max_batched_n(kind); }
+int gschur_cuda_max_batched_n(int kind) {
+    if (kind < 0 || kind > 3) return 0;
+    return max_schur_n(kind);
+}
 
 int gschur_cuda_batched_async(int kind, int n, int64_t batch, void* A, int lda, int64_t strideA, void* Z, int ldz,
                               int64_t strideZ, void* w, int scale, int maxiter, int32_t* info, uint32_t* stats,
@@ -421,7 +427,7 @@ int gschur_cuda_hessenberg_batched(int kind, int n, int64_t batch, void* A, int 
                                    void* Q, int ldq, int64_t strideQ, const int* devices, int ndev, uint32_t flags) {
     g_err.clear();
     int dummy = 0;
-    int rc = check_args(kind, n, batch, A, lda, strideA, Q, ldq, strideQ, &dummy);
+    int rc = check_args(kind, n, batch, A, lda, strideA, Q, ldq, strideQ, &dummy, false);
     if (rc) return rc;
     if (n == 0 || batch == 0) return 0;
     if (n > 1 && !tau) return fail(GSCHUR_ERR_ARG, "tau is NULL");

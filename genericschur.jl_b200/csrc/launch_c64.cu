@@ -1,5 +1,6 @@
 // Kernel instantiations for element kind c64 (one translation unit per kind keeps builds parallel).
-// n <= 64 goes to the warp-specialised kernel (fastqr.cuh); larger n to the generic block-synchronous one.
+// Schur requests go to the two-kernel path (gehrd.cuh + fastqr.cuh, n <= 128); Hessenberg-only requests and
+// anything forced by GSCHUR_FORCE_GENERIC to the block-synchronous single-kernel path (batched.cuh).
 #include <cstdlib>
 #include "fastqr.cuh"
 namespace gs {
@@ -8,6 +9,8 @@ int launch_c64(const BatchedParams& p, int dev_sms, cudaStream_t stream, std::st
     if (!force_generic && p.mode == MODE_SCHUR) {
         if (p.n <= 32) return launch_fast<cx<double>, 1>(p, dev_sms, stream, err);
         if (p.n <= 64) return launch_fast<cx<double>, 2>(p, dev_sms, stream, err);
+        if (p.n <= 96) return launch_fast<cx<double>, 3>(p, dev_sms, stream, err);
+        if (p.n <= 128) return launch_fast<cx<double>, 4>(p, dev_sms, stream, err);
     }
     return launch_t<cx<double>>(p, dev_sms, stream, err);
 }

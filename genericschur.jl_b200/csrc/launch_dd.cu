@@ -1,7 +1,16 @@
 // Kernel instantiations for element kind dd (one translation unit per kind keeps builds parallel).
-#include "batched.cuh"
+// Schur requests go to the two-kernel path (gehrd.cuh + fastqr.cuh, n <= 96); Hessenberg-only requests and
+// anything forced by GSCHUR_FORCE_GENERIC to the block-synchronous single-kernel path (batched.cuh).
+#include <cstdlib>
+#include "fastqr.cuh"
 namespace gs {
 int launch_dd(const BatchedParams& p, int dev_sms, cudaStream_t stream, std::string* err) {
+    static const bool force_generic = std::getenv("GSCHUR_FORCE_GENERIC") != nullptr;
+    if (!force_generic && p.mode == MODE_SCHUR) {
+        if (p.n <= 32) return launch_fast<dd_t, 1>(p, dev_sms, stream, err);
+        if (p.n <= 64) return launch_fast<dd_t, 2>(p, dev_sms, stream, err);
+        if (p.n <= 96) return launch_fast<dd_t, 3>(p, dev_sms, stream, err);
+    }
     return launch_t<dd_t>(p, dev_sms, stream, err);
 }
 }  // namespace gs
