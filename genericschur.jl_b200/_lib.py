@@ -27,6 +27,9 @@ EXPORTS = [
     "gschur_cuda_batched_async",
     "gschur_cuda_hessenberg_batched",
     "gschur_cuda_measure_fp64_peak",
+    "gschur_cuda_hessenberg_large",
+    "gschur_cuda_dgemm",
+    "gschur_cuda_large_last_error",
 ]
 
 _lib = None
@@ -62,6 +65,12 @@ def lib():
         L.gschur_cuda_hessenberg_batched.restype = ci
         L.gschur_cuda_measure_fp64_peak.argtypes = [vp, vp]
         L.gschur_cuda_measure_fp64_peak.restype = ci
+        cd = ctypes.c_double
+        L.gschur_cuda_hessenberg_large.argtypes = [ci, vp, ci, vp, vp, ci, u32]
+        L.gschur_cuda_hessenberg_large.restype = ci
+        L.gschur_cuda_dgemm.argtypes = [ci, ci, ci, ci, ci, cd, vp, ci, vp, ci, cd, vp, ci]
+        L.gschur_cuda_dgemm.restype = ci
+        L.gschur_cuda_large_last_error.restype = ctypes.c_char_p
         _lib = L
     return _lib
 

@@ -115,6 +115,25 @@ int gschur_cuda_hessenberg_batched(int kind, int n, int64_t batch,
                                    void* Q, int ldq, int64_t strideQ,
                                    const int* devices, int ndev, uint32_t flags);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Regime (2): ONE large Float64 matrix on one GPU (BASELINE config 4).  Host or device pointers
+ * (GSCHUR_FLAG_DEVICE_PTRS), blocking.
+ * ---------------------------------------------------------------------------------------------------------- */
+
+/*
+ * Blocked (compact-WY, DMMA-GEMM) Householder reduction A = Q H Q' of one n x n Float64 matrix.
+ * Replaces _hessenberg!(A) src/hessenberg.jl:3-17 + _materializeQ src/hessenberg.jl:150-166 for large n.
+ * A out: H on/above the sub-diagonal, reflector tails below; tau: n-1 (NULL ok); Q: n x n (NULL ok).
+ */
+int gschur_cuda_hessenberg_large(int n, double* A, int lda, double* tau, double* Q, int ldq, uint32_t flags);
+
+/* the library's FP64 tensor-core (DMMA) GEMM, C = alpha op(A) op(B) + beta C, device pointers; exposed for tests */
+int gschur_cuda_dgemm(int ta, int tb, int M, int N, int K, double alpha, const double* A, int lda,
+                      const double* B, int ldb, double beta, double* C, int ldc);
+
+/* text of the last error of the large-matrix entry points on this thread */
+const char* gschur_cuda_large_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif
