@@ -28,6 +28,7 @@ EXPORTS = [
     "gschur_cuda_hessenberg_batched",
     "gschur_cuda_measure_fp64_peak",
     "gschur_cuda_hessenberg_large",
+    "gschur_cuda_large",
     "gschur_cuda_dgemm",
     "gschur_cuda_large_last_error",
 ]
@@ -68,6 +69,8 @@ def lib():
         cd = ctypes.c_double
         L.gschur_cuda_hessenberg_large.argtypes = [ci, vp, ci, vp, vp, ci, u32]
         L.gschur_cuda_hessenberg_large.restype = ci
+        L.gschur_cuda_large.argtypes = [ci, vp, ci, vp, ci, vp, ci, vp, vp, u32]
+        L.gschur_cuda_large.restype = ci
         L.gschur_cuda_dgemm.argtypes = [ci, ci, ci, ci, ci, cd, vp, ci, vp, ci, cd, vp, ci]
         L.gschur_cuda_dgemm.restype = ci
         L.gschur_cuda_large_last_error.restype = ctypes.c_char_p

@@ -1,0 +1,402 @@
+// Regime (2), part 2: QR iteration on ONE large upper Hessenberg Float64 matrix.
+//
+// The reference's sweep (doubleShiftQR!, src/GenericSchur.jl:837-952) chases one 3x3 bulge down the whole matrix,
+// touching 3 rows x n columns and 3 columns x n rows per step — 15 million strictly sequential steps at n = 4096.
+// Here the same 3x3 double-shift bulges (same reflector, same first-column formula, same deflation criterion) are
+//   * chased NB at a time as a chain (bulge b trails bulge b-1 by 4 columns; all advance in lock-step, one warp per
+//     bulge, on disjoint rows in the left phase and disjoint columns in the right phase), with shift pairs taken
+//     from the eigenvalues of the trailing 2 NB x 2 NB block of the active window (small-bulge multishift);
+//   * confined to a diagonal window held in shared memory while the product U of their reflectors is accumulated;
+//   * applied to everything outside the window — the rest of H's rows and columns and all of Z — as FP64 DMMA GEMMs
+//     with U (dgemm.cuh).
+// Active blocks of order <= 128 are finished by the batched kernel (fastqr.cuh) and back-transformed with GEMMs.
+// Deflation uses the reference's test (Ahues-Tisseur with its `aa + bb`, src/GenericSchur.jl:563-600).
+#pragma once
+#include <algorithm>
+#include <complex>
+#include <vector>
+#include "batched.cuh"
+#include "large_gehrd.cuh"
+
+namespace gs {
+
+constexpr int LQ_NB = 8;        // bulges per chain (2 NB shifts per sweep)
+constexpr int LQ_W = 96;        // maximum window order
+constexpr int LQ_LDW = 97;      // shared-memory leading dimension (odd: conflict-free rows and columns)
+constexpr int LQ_SMALL = 128;   // active blocks up to this order go to the batched kernel
+
+struct LqScan {
+    int istart;   // 1-based start of the active block ending at iend
+};
+
+// Largest k in (1, iend] whose sub-diagonal H[k,k-1] is negligible by the reference's criterion; istart = k (or 1).
+// One CTA; the split entry is set to zero as the reference does (src/GenericSchur.jl:604-606).
+__global__ void __launch_bounds__(1024) lq_scan_kernel(double* H, int n, int iend, LqScan* out) {
+    __shared__ int best;
+    if (threadIdx.x == 0) best = 1;
+    __syncthreads();
+    const double eps = 2.220446049250313e-16;
+    const double smallnum = 2.2250738585072014e-308 * ((double)n / eps);
+#define HL(i, j) H[((size_t)(i)-1) + ((size_t)(j)-1) * n]
+    for (int base = iend; base >= 2; base -= 1024) {
+        const int k = base - threadIdx.x;
+        bool hit = false;
+        if (k >= 2) {
+            const double h = fabs(HL(k, k - 1));
+            if (h < smallnum) hit = true;
+            else {
+                const double Hkk = HL(k, k), Hk1 = HL(k - 1, k - 1);
+                double t = fabs(Hk1) + fabs(Hkk);
+                if (t == 0.0) {
+                    if (k > 2) t += fabs(HL(k - 1, k - 2));
+                    if (k + 1 <= n) t += fabs(HL(k + 1, k));
+                }
+                if (h <= t * eps) {
+                    const double o = fabs(HL(k - 1, k));
+                    const double ab = fmax(h, o), ba = fmin(h, o);
+                    const double d1 = fabs(Hkk), d2 = fabs(Hk1 - Hkk);
+                    const double aa = fmax(d1, d2), bb = fmin(d1, d2);
+                    const double s = aa + bb;
+                    if (ba * (ab / s) <= fmax(smallnum, eps * (bb * (aa / s)))) hit = true;
+                }
+            }
+        }
+        if (hit) atomicMax(&best, k);
+        __syncthreads();
+        if (best > 1) break;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out->istart = best;
+        if (best > 1) HL(best, best - 1) = 0.0;
+    }
+#undef HL
+}
+
+// Chase the chain through one window.  Bulge b at time tau sits at column p = L + tau - 4 b (1-based); it is active
+// while L <= p <= I-1.  The window is rows/columns wlo..whi of H.  U (wsz x wsz, ld LQ_W, global) receives the
+// accumulated orthogonal factor: H_window <- U' H_window U.
+__global__ void __launch_bounds__(32 * LQ_NB) lq_chase_kernel(double* H, int n, int L, int I, const double* shifts,
+                                                             int tau0, int M, int wlo, int whi, double* Uout) {
+    extern __shared__ double sm[];
+    double* Hw = sm;                       // LQ_W x LQ_LDW
+    double* Uw = sm + LQ_W * LQ_LDW;       // LQ_W x LQ_LDW
+    const int tid = threadIdx.x, lane = tid & 31, b = tid >> 5;
+    const int wsz = whi - wlo + 1;
+#define HW(i, j) Hw[((i)-wlo) + ((j)-wlo) * LQ_LDW]          // global 1-based indices
+#define UW(i, j) Uw[(i) + (j)*LQ_LDW]                        // local 0-based indices
+    for (int e = tid; e < wsz * wsz; e += blockDim.x) {
+        const int i = e % wsz, j = e / wsz;
+        Hw[i + j * LQ_LDW] = H[(size_t)(wlo - 1 + i) + (size_t)(wlo - 1 + j) * n];
+        Uw[i + j * LQ_LDW] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    const double r1r = shifts[4 * b + 0], r1i = shifts[4 * b + 1], r2r = shifts[4 * b + 2], r2i = shifts[4 * b + 3];
+    for (int tau = tau0; tau < tau0 + M; ++tau) {
+        const int p = L + tau - 4 * b;
+        const bool active = (p >= L && p <= I - 1);
+        const int nr = (I - p + 1 < 3) ? I - p + 1 : 3;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, tau1 = 0.0;
+        if (active) {
+            if (p == L) {
+                // first column of (H - s1)(H - s2), src/GenericSchur.jl:855-863
+                const double hmm = HW(L, L);
+                double H21s = HW(L + 1, L);
+                double s = fabs(hmm - r2r) + fabs(r2i) + fabs(H21s);
+                H21s = H21s / s;
+                v0 = H21s * HW(L, L + 1) + (hmm - r1r) * ((hmm - r2r) / s) - r1i * (r2i / s);
+                v1 = H21s * (hmm + HW(L + 1, L + 1) - r1r - r2r);
+                v2 = (nr == 3) ? H21s * HW(L + 2, L + 1) : 0.0;
+                s = fabs(v0) + fabs(v1) + fabs(v2);
+                v0 /= s;
+                v1 /= s;
+                v2 /= s;
+            } else {
+                v0 = HW(p, p - 1);
+                v1 = HW(p + 1, p - 1);
+                v2 = (nr == 3) ? HW(p + 2, p - 1) : 0.0;
+            }
+            tau1 = reflector_real_small(v0, v1, v2, nr);
+        }
+        __syncthreads();
+        const double tau2 = tau1 * v1, tau3 = tau1 * v2;
+        // ---- left phase: rows p..p+nr-1, columns p..whi (disjoint rows across bulges) ----
+        if (active) {
+            for (int j = p + lane; j <= whi; j += 32) {
+                const double a = HW(p, j), bb = HW(p + 1, j), c = (nr == 3) ? HW(p + 2, j) : 0.0;
+                const double ss = a + v1 * bb + v2 * c;
+                HW(p, j) = a - ss * tau1;
+                HW(p + 1, j) = bb - ss * tau2;
+                if (nr == 3) HW(p + 2, j) = c - ss * tau3;
+            }
+            if (lane == 0 && p > L) {
+                HW(p, p - 1) = v0;
+                HW(p + 1, p - 1) = 0.0;
+                if (nr == 3) HW(p + 2, p - 1) = 0.0;
+            }
+        }
+        __syncthreads();
+        // ---- right phase: columns p..p+nr-1, rows wlo..min(p+3, I) (disjoint columns across bulges), and U ----
+        if (active) {
+            const int rmax = (p + 3 < I) ? p + 3 : I;
+            for (int r = wlo + lane; r <= rmax; r += 32) {
+                const double a = HW(r, p), bb = HW(r, p + 1), c = (nr == 3) ? HW(r, p + 2) : 0.0;
+                const double ss = a + v1 * bb + v2 * c;
+                HW(r, p) = a - ss * tau1;
+                HW(r, p + 1) = bb - ss * tau2;
+                if (nr == 3) HW(r, p + 2) = c - ss * tau3;
+            }
+            const int pc = p - wlo;
+            for (int r = lane; r < wsz; r += 32) {
+                const double a = UW(r, pc), bb = UW(r, pc + 1), c = (nr == 3) ? UW(r, pc + 2) : 0.0;
+                const double ss = a + v1 * bb + v2 * c;
+                UW(r, pc) = a - ss * tau1;
+                UW(r, pc + 1) = bb - ss * tau2;
+                if (nr == 3) UW(r, pc + 2) = c - ss * tau3;
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < wsz * wsz; e += blockDim.x) {
+        const int i = e % wsz, j = e / wsz;
+        H[(size_t)(wlo - 1 + i) + (size_t)(wlo - 1 + j) * n] = Hw[i + j * LQ_LDW];
+        Uout[i + j * LQ_W] = Uw[i + j * LQ_LDW];
+    }
+#undef HW
+#undef UW
+}
+
+__global__ void lq_copy_block_kernel(const double* src, int lds, double* dst, int ldd, int rows, int cols) {
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < (size_t)rows * cols) {
+        const int i = idx % rows, j = idx / rows;
+        dst[(size_t)i + (size_t)j * ldd] = src[(size_t)i + (size_t)j * lds];
+    }
+}
+__global__ void lq_eye_kernel(double* dst, int ld, int m) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < m * m) dst[(idx % m) + (size_t)(idx / m) * ld] = ((idx % m) == (idx / m)) ? 1.0 : 0.0;
+}
+// eigenvalues of a quasi-triangular T in standard form (2x2 blocks: a +- i sqrt|b| sqrt|c|)
+__global__ void lq_eigs_kernel(const double* T, int n, double* w) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;   // 0-based
+    if (j >= n) return;
+#define TT(i, k) T[(size_t)(i) + (size_t)(k)*n]
+    const bool sub_below = (j + 1 < n) && TT(j + 1, j) != 0.0;
+    const bool sub_above = (j >= 1) && TT(j, j - 1) != 0.0;
+    double re = TT(j, j), im = 0.0;
+    if (sub_below) im = sqrt(fabs(TT(j, j + 1))) * sqrt(fabs(TT(j + 1, j)));
+    else if (sub_above) im = -sqrt(fabs(TT(j - 1, j))) * sqrt(fabs(TT(j, j - 1)));
+    w[2 * j] = re;
+    w[2 * j + 1] = im;
+#undef TT
+}
+
+inline void lq_copy(cudaStream_t s, const double* src, int lds, double* dst, int ldd, int rows, int cols) {
+    if (rows <= 0 || cols <= 0) return;
+    const size_t tot = (size_t)rows * cols;
+    lq_copy_block_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(src, lds, dst, ldd, rows, cols);
+    note_launch();
+}
+
+struct LargeQrStats {
+    long sweeps = 0, windows = 0, small_blocks = 0;
+};
+
+// H (n x n Hessenberg, zeros below the sub-diagonal), Z (n x n or null) on the device.  Returns 0, or k > 0 when the
+// iteration limit is hit with the active block ending at row k.  w: 2n doubles (device).
+inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::string* err, LargeQrStats* stats) {
+    const size_t wbuf = (size_t)LQ_SMALL * std::max(n, LQ_SMALL);
+    double* base = nullptr;
+    // scratch: U (LQ_SMALL^2), tmp (LQ_SMALL x n), blk (LQ_SMALL^2), zblk (LQ_SMALL^2), wblk, shifts, scan
+    const size_t total = 3 * (size_t)LQ_SMALL * LQ_SMALL + wbuf + 2 * LQ_SMALL + 4 * LQ_NB + 64;
+    LG_TRY(cudaMallocAsync((void**)&base, total * sizeof(double), s));
+    double* dU = base;
+    double* dBlk = dU + (size_t)LQ_SMALL * LQ_SMALL;
+    double* dZb = dBlk + (size_t)LQ_SMALL * LQ_SMALL;
+    double* dTmp = dZb + (size_t)LQ_SMALL * LQ_SMALL;
+    double* dWb = dTmp + wbuf;
+    double* dShift = dWb + 2 * LQ_SMALL;
+    LqScan* dScan = reinterpret_cast<LqScan*>(dShift + 4 * LQ_NB);
+    int* dInfo = reinterpret_cast<int*>(dScan + 1);
+    unsigned long long* dCounter = reinterpret_cast<unsigned long long*>(dScan + 4);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t chase_smem = 2 * (size_t)LQ_W * LQ_LDW * sizeof(double);
+    LG_TRY(cudaFuncSetAttribute(lq_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chase_smem));
+
+    auto run_small = [&](double* blk, int m, double* zb, double* wb, bool wantz) -> int {
+        // batched kernel on one m x m Hessenberg block: blk <- T, zb <- Z_blk (in: identity), wb <- eigenvalues
+        BatchedParams p{};
+        p.A = blk;
+        p.Z = wantz ? zb : nullptr;
+        p.w = wb;
+        p.tau = nullptr;
+        p.strideA = (long long)m * m;
+        p.strideZ = (long long)m * m;
+        p.batch = 1;
+        p.lda = m;
+        p.ldz = m;
+        p.n = m;
+        p.scale = 0;
+        p.maxiter = 0;
+        p.mode = MODE_SCHUR;
+        p.flags = F_HESS_INPUT;
+        p.info = dInfo;
+        p.stats = nullptr;
+        p.counter = dCounter;
+        p.scratch = nullptr;
+        cudaMemsetAsync(dCounter, 0, sizeof(unsigned long long), s);
+        std::string e2;
+        int rc = launch_f64(p, sms, s, &e2);
+        if (rc) *err = e2;
+        return rc;
+    };
+    // apply an orthogonal m x m factor Q (ld ldq) that transformed rows/cols lo..hi (1-based):
+    //   H[lo:hi, hi+1:n] <- Q' H[...],  H[1:lo-1, lo:hi] <- H[...] Q,  Z[:, lo:hi] <- Z[...] Q
+    auto apply_outside = [&](const double* Q, int ldq, int lo, int hi) -> int {
+        const int m = hi - lo + 1;
+        const int nr = n - hi;
+        if (nr > 0) {
+            double* C = H + (size_t)(lo - 1) + (size_t)hi * n;
+            LG_TRY(dgemm(s, true, false, m, nr, m, 1.0, Q, ldq, C, n, 0.0, dTmp, m));
+            lq_copy(s, dTmp, m, C, n, m, nr);
+        }
+        const int nt = lo - 1;
+        if (nt > 0) {
+            double* C = H + (size_t)(lo - 1) * n;
+            LG_TRY(dgemm(s, false, false, nt, m, m, 1.0, C, n, Q, ldq, 0.0, dTmp, nt));
+            lq_copy(s, dTmp, nt, C, n, nt, m);
+        }
+        if (Z) {
+            double* C = Z + (size_t)(lo - 1) * n;
+            LG_TRY(dgemm(s, false, false, n, m, m, 1.0, C, n, Q, ldq, 0.0, dTmp, n));
+            lq_copy(s, dTmp, n, C, n, n, m);
+        }
+        return 0;
+    };
+
+    int iend = n;
+    long sweeps_total = 0;
+    int since_deflation = 0;
+    const long maxsweeps = 30L * n + 100;
+    std::vector<double> hshift(2 * 2 * LQ_NB), hpairs(4 * LQ_NB);
+    int rc_final = 0;
+    while (iend >= 1) {
+        lq_scan_kernel<<<1, 1024, 0, s>>>(H, n, iend, dScan);
+        note_launch();
+        LqScan hs;
+        LG_TRY(cudaMemcpyAsync(&hs, dScan, sizeof(LqScan), cudaMemcpyDeviceToHost, s));
+        LG_TRY(cudaStreamSynchronize(s));
+        const int istart = hs.istart;
+        const int nw = iend - istart + 1;
+        if (nw <= LQ_SMALL) {
+            // finish the block with the batched kernel, back-transform with GEMMs
+            lq_copy(s, H + (size_t)(istart - 1) + (size_t)(istart - 1) * n, n, dBlk, nw, nw, nw);
+            lq_eye_kernel<<<(nw * nw + 255) / 256, 256, 0, s>>>(dZb, nw, nw);
+            note_launch();
+            int rc = run_small(dBlk, nw, dZb, dWb, true);
+            if (rc) { cudaFreeAsync(base, s); return -2; }
+            int hinfo = 0;
+            LG_TRY(cudaMemcpyAsync(&hinfo, dInfo, sizeof(int), cudaMemcpyDeviceToHost, s));
+            LG_TRY(cudaStreamSynchronize(s));
+            if (hinfo != 0) { rc_final = iend; break; }
+            lq_copy(s, dBlk, nw, H + (size_t)(istart - 1) + (size_t)(istart - 1) * n, n, nw, nw);
+            if (nw > 1) {
+                rc = apply_outside(dZb, nw, istart, iend);
+                if (rc) { cudaFreeAsync(base, s); return rc; }
+            }
+            if (stats) stats->small_blocks += 1;
+            iend = istart - 1;
+            since_deflation = 0;
+            continue;
+        }
+        if (++sweeps_total > maxsweeps) { rc_final = iend; break; }
+        since_deflation += 1;
+        // ---- shifts: eigenvalues of the trailing 2 NB x 2 NB block of the active window ----
+        const int ns = 2 * LQ_NB;
+        lq_copy(s, H + (size_t)(iend - ns) + (size_t)(iend - ns) * n, n, dBlk, ns, ns, ns);
+        if (since_deflation % 6 == 0) {
+            // exceptional shifts (in the spirit of src/GenericSchur.jl:614-627): perturb the trailing diagonal
+            std::vector<double> hb((size_t)ns * ns);
+            LG_TRY(cudaMemcpyAsync(hb.data(), dBlk, sizeof(double) * ns * ns, cudaMemcpyDeviceToHost, s));
+            LG_TRY(cudaStreamSynchronize(s));
+            for (int j = 0; j < ns; ++j) {
+                const double sub = (j > 0) ? fabs(hb[j + (size_t)(j - 1) * ns]) : fabs(hb[1]);
+                hshift[2 * j] = hb[j + (size_t)j * ns] + 0.75 * sub;
+                hshift[2 * j + 1] = 0.0;
+            }
+        } else {
+            int rc = run_small(dBlk, ns, nullptr, dWb, false);
+            if (rc) { cudaFreeAsync(base, s); return -2; }
+            LG_TRY(cudaMemcpyAsync(hshift.data(), dWb, sizeof(double) * 2 * ns, cudaMemcpyDeviceToHost, s));
+            LG_TRY(cudaStreamSynchronize(s));
+        }
+        // pair the shifts: conjugate pairs stay together, real ones are paired up (a leftover real is doubled)
+        {
+            std::vector<std::complex<double>> cp, re;
+            for (int j = 0; j < ns; ++j) {
+                std::complex<double> z(hshift[2 * j], hshift[2 * j + 1]);
+                if (z.imag() != 0.0) cp.push_back(z);
+                else re.push_back(z);
+            }
+            int np = 0;
+            for (size_t j = 0; j + 1 < cp.size() && np < LQ_NB; j += 2, ++np) {
+                std::complex<double> a = cp[j];
+                hpairs[4 * np] = a.real();
+                hpairs[4 * np + 1] = fabs(a.imag());
+                hpairs[4 * np + 2] = a.real();
+                hpairs[4 * np + 3] = -fabs(a.imag());
+            }
+            std::sort(re.begin(), re.end(), [](const std::complex<double>& x, const std::complex<double>& y) { return x.real() < y.real(); });
+            for (size_t j = 0; j < re.size() && np < LQ_NB; j += 2, ++np) {
+                const double a = re[j].real(), b2 = (j + 1 < re.size()) ? re[j + 1].real() : re[j].real();
+                hpairs[4 * np] = a;
+                hpairs[4 * np + 1] = 0.0;
+                hpairs[4 * np + 2] = b2;
+                hpairs[4 * np + 3] = 0.0;
+            }
+            for (; np < LQ_NB; ++np) {   // not enough shifts (cannot happen with ns = 2 NB): repeat the last pair
+                for (int q = 0; q < 4; ++q) hpairs[4 * np + q] = hpairs[4 * (np - 1) + q];
+            }
+        }
+        LG_TRY(cudaMemcpyAsync(dShift, hpairs.data(), sizeof(double) * 4 * LQ_NB, cudaMemcpyHostToDevice, s));
+        // ---- chase the chain from the top (L = istart) to the bottom (I = iend) ----
+        const int L = istart, I = iend;
+        const int tau_end = (I - 1 - L) + 4 * (LQ_NB - 1);        // last time step with an active bulge
+        int tau0 = 0;
+        while (tau0 <= tau_end) {
+            // window for M steps: from the trailing active bulge's column - 1 to the leading active bulge's end + 3
+            int M = LQ_W - (4 * (LQ_NB - 1) + 6);
+            if (tau0 + M - 1 > tau_end) M = tau_end - tau0 + 1;
+            int pmin = 1 << 30, pmax = -1;
+            for (int b = 0; b < LQ_NB; ++b) {
+                const int p0 = L + tau0 - 4 * b, p1 = L + tau0 + M - 1 - 4 * b;
+                if (p1 < L || p0 > I - 1) continue;
+                pmin = std::min(pmin, std::max(p0, L));
+                pmax = std::max(pmax, std::min(p1, I - 1));
+            }
+            if (pmax < 0) { tau0 += M; continue; }
+            const int wlo = std::max(L, pmin - 1), whi = std::min(I, pmax + 3);
+            const int wsz = whi - wlo + 1;
+            if (wsz > LQ_W) { *err = "internal: chase window too large"; cudaFreeAsync(base, s); return -2; }
+            lq_chase_kernel<<<1, 32 * LQ_NB, chase_smem, s>>>(H, n, L, I, dShift, tau0, M, wlo, whi, dU);
+            note_launch();
+            int rc = apply_outside(dU, LQ_W, wlo, whi);
+            if (rc) { cudaFreeAsync(base, s); return rc; }
+            if (stats) stats->windows += 1;
+            tau0 += M;
+        }
+        if (stats) stats->sweeps += 1;
+    }
+    if (rc_final == 0 && w) {
+        lq_eigs_kernel<<<(n + 255) / 256, 256, 0, s>>>(H, n, w);
+        note_launch();
+    }
+    LG_TRY(cudaStreamSynchronize(s));
+    cudaFreeAsync(base, s);
+    return rc_final;
+}
+
+}  // namespace gs

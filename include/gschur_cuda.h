@@ -127,6 +127,18 @@ int gschur_cuda_hessenberg_batched(int kind, int n, int64_t batch,
  */
 int gschur_cuda_hessenberg_large(int n, double* A, int lda, double* tau, double* Q, int ldq, uint32_t flags);
 
+/*
+ * Schur decomposition of ONE large n x n Float64 matrix: blocked Hessenberg + Q, then small-bulge multishift QR
+ * (chains of the reference's 3x3 double-shift bulges chased through diagonal windows, reflectors accumulated and
+ * applied to the rest of H and to Z as DMMA GEMMs), active blocks of order <= 128 finished by the batched kernel.
+ * Replaces gschur!(A::StridedMatrix{Float64}; wantZ, scale) src/GenericSchur.jl:805-835 for large n.
+ *   A in/out: matrix -> quasi-triangular T (standard-form 2x2 blocks); Z out (NULL = wantZ false); w: n complex.
+ *   info (NULL ok): 0 or k > 0 (iteration limit, active block ends at row k); stats3 (NULL ok): sweeps, windows,
+ *   small blocks.  Returns 0, 1 (not converged) or a negative error.
+ */
+int gschur_cuda_large(int n, double* A, int lda, double* Z, int ldz, double* w, int scale, int* info,
+                      long long* stats3, uint32_t flags);
+
 /* the library's FP64 tensor-core (DMMA) GEMM, C = alpha op(A) op(B) + beta C, device pointers; exposed for tests */
 int gschur_cuda_dgemm(int ta, int tb, int M, int N, int K, double alpha, const double* A, int lda,
                       const double* B, int ldb, double beta, double* C, int ldc);
