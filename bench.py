@@ -139,6 +139,94 @@ def cpu_baseline(kind, n, batch, seed, cores=None, steps=1):
                       f"oracle/ C++ restatement of gschur! (Julia is not installed; see DESIGN.md)"}, sample, best
 
 
+def other_workloads(gs, torch, skip):
+    """Informational single-shot timings (device-resident, CUDA events, one warm-up) of the other BASELINE configs:
+    cfg2 (16384 x 32x32 Float64), 64x64 Float64, cfg5 (4096 x 96x96 complex double-double), cfg4 (one 4096x4096
+    Float64: GFLOP/s on the nominal 25 n^3)."""
+    import ctypes
+    out = {}
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def timed(fn, reps=2):
+        best = None
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            best = ms if best is None else min(best, ms)
+        return best
+
+    for name, (kind, n, batch, flops, desc) in WORKLOADS.items():
+        if name == skip:
+            continue
+        dt = torch.complex128 if kind == 1 else torch.float64
+        A0 = torch.rand((batch, n, n), dtype=dt, device="cuda")
+        A = torch.empty_like(A0)
+        Z = torch.empty_like(A0)
+        w = torch.empty((batch, n), dtype=torch.complex128, device="cuda")
+        info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+
+        def fn():
+            A.copy_(A0)
+            gs.gschur_device_(kind, n, batch, A.data_ptr(), Z.data_ptr(), w.data_ptr(), info.data_ptr(), stream=stream)
+        ms = timed(fn) - timed(lambda: A.copy_(A0))
+        out[name] = {"workload": desc, "matrices_per_s": batch / (ms * 1e-3), "ms": ms,
+                     "nominal_tflops": flops * batch / (ms * 1e-3) / 1e12, "unconverged": int((info != 0).sum().item())}
+        del A0, A, Z, w, info
+        torch.cuda.empty_cache()
+    # cfg5: complex double-double, limbs (re.hi, re.lo, im.hi, im.lo) innermost
+    n, batch = 96, 4096
+    hi = torch.rand((batch, n, n, 2), dtype=torch.float64, device="cuda")
+    lo = (torch.rand((batch, n, n, 2), dtype=torch.float64, device="cuda") - 0.5) * 2.0 ** -53 * hi
+    A0 = torch.stack([hi[..., 0], lo[..., 0], hi[..., 1], lo[..., 1]], dim=-1).contiguous()   # (batch, n, n, 4)
+    A = torch.empty_like(A0)
+    Z = torch.empty_like(A0)
+    w = torch.empty((batch, n, 4), dtype=torch.float64, device="cuda")
+    info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+
+    def fn5():
+        A.copy_(A0)
+        gs.gschur_device_(gs.CDD, n, batch, A.data_ptr(), Z.data_ptr(), w.data_ptr(), info.data_ptr(), stream=stream)
+    ms = timed(fn5, reps=1)
+    out["cfg5"] = {"workload": "4096 x 96x96 Complex{double-double}, with Z", "matrices_per_s": batch / (ms * 1e-3), "ms": ms,
+                   "dd_gflops_nominal": 88 * n ** 3 * batch / (ms * 1e-3) / 1e9, "unconverged": int((info != 0).sum().item())}
+    del A0, A, Z, w, info, hi, lo
+    torch.cuda.empty_cache()
+    # cfg4: one 4096 x 4096 Float64 matrix
+    from genericschur_jl_b200 import _lib
+    L = _lib.lib()
+    n = 4096
+    A0 = torch.rand((n, n), dtype=torch.float64, device="cuda")
+    A = torch.empty_like(A0)
+    Z = torch.empty_like(A0)
+    w = torch.empty((n,), dtype=torch.complex128, device="cuda")
+    inf = ctypes.c_int(0)
+    st = (ctypes.c_longlong * 3)()
+
+    def fn4():
+        A.copy_(A0)
+        rc = L.gschur_cuda_large(n, ctypes.c_void_p(A.data_ptr()), n, ctypes.c_void_p(Z.data_ptr()), n,
+                                 ctypes.c_void_p(w.data_ptr()), 1, ctypes.byref(inf), st, 1)
+        assert rc == 0, rc
+    ms = timed(fn4, reps=1)
+    out["cfg4"] = {"workload": "one 4096x4096 Float64: Hessenberg + real Schur with Z", "ms": ms,
+                   "gflops_nominal_25n3": 25.0 * n ** 3 / (ms * 1e-3) / 1e9, "sweeps": int(st[0]), "windows": int(st[1]),
+                   "small_blocks": int(st[2])}
+
+    def fh():
+        A.copy_(A0)
+        rc = L.gschur_cuda_hessenberg_large(n, ctypes.c_void_p(A.data_ptr()), n, None, ctypes.c_void_p(Z.data_ptr()), n, 1)
+        assert rc == 0, rc
+    msh = timed(fh, reps=2)
+    out["cfg4"]["hessenberg_plus_q_ms"] = msh
+    out["cfg4"]["panel_gemv_algorithmic_GB"] = 8.0 / 3.0 * n ** 3 / 1e9
+    return out
+
+
 def run_reference(args):
     kind, n, batch, flops, desc = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
@@ -183,6 +271,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (development only)")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the informational runs of the other BASELINE configs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -297,6 +386,11 @@ def main():
                "checksum": checksum}
         del Ah, Zh
 
+    others = None
+    if rank == 0 and world == 1 and not args.no_others:
+        del A0, A, Z, w, info, stats
+        torch.cuda.empty_cache()
+        others = other_workloads(gs, torch, args.workload)
     if rank == 0:
         hbm_peak, hbm_src = measured_peaks()
         fp64_peak, _ = gs.measure_fp64_peak()
@@ -326,7 +420,7 @@ def main():
                        "l2_policy": "inputs_exceed_l2" if batch * n * n * esz > 2 * 126e6 else "inputs_fit_l2",
                        "sharding": "independent per-GPU shards, no collective"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "wall_s_timed_region": t_wall,
+            "wall_s_timed_region": t_wall, "other_workloads": others,
         }
         print(json.dumps(line))
     if world > 1:

@@ -182,15 +182,35 @@ def _eig_array(kind, n, batch):
     return np.zeros((4, n) + shape_b, dtype=np.float64, order="F").view(CDDArray)
 
 
+def _gschur_large_(A, wantZ, scale, check):
+    """One large Float64 matrix (n > 128): blocked Hessenberg + multi-bulge QR with GEMM updates (regime 2)."""
+    n = A.shape[0]
+    Z = np.zeros_like(A) if wantZ else None
+    w = np.zeros(n, dtype=np.complex128)
+    info = ctypes.c_int(0)
+    st = (ctypes.c_longlong * 3)()
+    rc = _lib.lib().gschur_cuda_large(n, _ptr(A), n, _ptr(Z), n, _ptr(w), int(bool(scale)), ctypes.byref(info), st, 0)
+    if rc < 0:
+        raise RuntimeError(f"libgschur_cuda error {rc}: {_lib.lib().gschur_cuda_large_last_error().decode()}")
+    if rc > 0 and check:
+        raise UnconvergedException(f"iteration limit reached (active block ends at row {info.value})")
+    if not wantZ:
+        Z = np.zeros((0, 0), dtype=A.dtype)
+    return Schur(A, Z, w, info=int(info.value), stats=np.array(list(st), dtype=np.int64))
+
+
 def gschur_(A, wantZ=True, scale=True, maxiter=None, devices=None, check=True, flags=0, Z=None):
     """gschur!(A; wantZ, scale, maxiter): A (Fortran-ordered, see module doc) is overwritten by T.
 
     Works on one matrix or on a batch (trailing axis).  Returns Schur(T=A, Z, values[, info, stats]).
     `devices`: list of CUDA device ordinals the batch is split over (contiguous slices, no collective).
+    A single Float64 matrix larger than the batched kernels take (n > 128) goes to the large-matrix path.
     """
     kind, lead, n, batch = _kind_and_shape(A)
     if not (A.flags.f_contiguous and A.flags.writeable):
         raise ArgumentError("A must be a writeable Fortran-ordered (column-major) array")
+    if kind == F64 and batch is None and n > max_batched_n(F64) and flags == 0 and Z is None:
+        return _gschur_large_(A, wantZ, scale, check)
     nb = 1 if batch is None else batch
     if wantZ:
         if Z is None:

@@ -333,7 +333,96 @@ def test_larger_n_two_kernel_path(gs, O):
         S2 = gs.gschur(A, wantZ=False)
         assert np.array_equal(S2.T, S.T)
     with pytest.raises(RuntimeError):
-        gs.gschur(np.asfortranarray(rng.random((129, 129))))
+        gs.gschur(np.asfortranarray(rng.random((129, 129)) + 0j))      # no large-matrix path for ComplexF64
+
+
+def test_dmma_gemm(gs):
+    """The library's FP64 tensor-core GEMM (mma.sync m8n8k4, SASS DMMA) against torch.matmul in float64."""
+    import ctypes
+    import torch
+    from genericschur_jl_b200 import _lib
+    L = _lib.lib()
+    for ta, tb, M, N, K in [(0, 0, 100, 70, 50), (1, 0, 33, 129, 200), (0, 1, 257, 64, 32), (1, 1, 65, 65, 17),
+                            (0, 0, 1000, 96, 96), (1, 0, 32, 900, 1111)]:
+        A = torch.rand((K, M) if not ta else (M, K), dtype=torch.float64, device="cuda")   # row-major (c, r) == col-major (r, c)
+        B = torch.rand((N, K) if not tb else (K, N), dtype=torch.float64, device="cuda")
+        C = torch.rand((N, M), dtype=torch.float64, device="cuda")
+        C0 = C.clone()
+        rc = L.gschur_cuda_dgemm(ta, tb, M, N, K, 1.5, ctypes.c_void_p(A.data_ptr()), A.shape[1],
+                                 ctypes.c_void_p(B.data_ptr()), B.shape[1], 0.5, ctypes.c_void_p(C.data_ptr()), M)
+        assert rc == 0
+        opA = A.T if not ta else A
+        opB = B.T if not tb else B
+        ref = 1.5 * opA @ opB + 0.5 * C0.T
+        assert (C.T - ref).abs().max().item() < 1e-12 * K
+
+
+def _large_checks(A0, S, n):
+    T, Z, w = S.T, S.Z, S.values
+    assert S.info == 0
+    assert not np.any(np.tril(T, -2))
+    sub = np.diag(T, -1)
+    for j in np.nonzero(sub)[0]:       # every 2x2 block in standard form (test/real.jl:3-22)
+        assert T[j, j] == T[j + 1, j + 1] and T[j, j + 1] * T[j + 1, j] < 0
+    # acceptance ratios of test/real.jl:40,43 (Float64 evaluation: MPFR would take minutes at this size; the margin
+    # to the tolerance of 10 is two orders of magnitude)
+    berr = np.linalg.norm(A0 - Z @ T @ Z.T) / (n * np.linalg.norm(A0) * ULP)
+    oerr = np.linalg.norm(Z.T @ Z - np.eye(n)) / (n * ULP)
+    assert berr < 10 and oerr < 10, (berr, oerr)
+    assert abs(w.sum() - np.trace(A0)) < 1e-9 * n
+    return berr, oerr
+
+
+def test_large_matrix_path(gs, O):
+    """Regime 2 (gschur_cuda_large): n > 128 Float64.  Checked against the oracle (the reference's unblocked
+    algorithm) at n = 200 with the eigvalscond-scaled eigenvalue tolerance, by invariants at n = 512."""
+    rng = np.random.default_rng(1234 + 4)
+    n = 200
+    A0 = np.asfortranarray(rng.random((n, n)))
+    S = gs.gschur(A0)
+    _large_checks(A0, S, n)
+    _check_one(O, A0, S.T, S.Z, S.values, 0, 10, "large200")
+    n = 512
+    A0 = np.asfortranarray(rng.random((n, n)))
+    S = gs.gschur(A0)
+    _large_checks(A0, S, n)
+    ev = np.linalg.eigvals(A0)
+    from scipy.optimize import linear_sum_assignment
+    D = np.abs(S.values[None, :] - ev[:, None])
+    r, c = linear_sum_assignment(D)
+    assert D[r, c].max() < 1e-10
+    S2 = gs.gschur(A0, wantZ=False)
+    assert S2.Z.shape == (0, 0)
+    D = np.abs(S2.values[None, :] - ev[:, None])
+    r, c = linear_sum_assignment(D)
+    assert D[r, c].max() < 1e-10
+
+
+def test_large_hessenberg(gs):
+    """Blocked WY Hessenberg + Q for one large matrix (hesstest of test/real.jl:76-99 at n = 700)."""
+    import ctypes
+    from genericschur_jl_b200 import _lib
+    rng = np.random.default_rng(3)
+    n = 700
+    A0 = rng.random((n, n))
+    A = np.asfortranarray(A0.copy())
+    Q = np.zeros((n, n), order="F")
+    tau = np.zeros(n)
+    vp = ctypes.c_void_p
+    rc = _lib.lib().gschur_cuda_hessenberg_large(n, A.ctypes.data_as(vp), n, tau.ctypes.data_as(vp), Q.ctypes.data_as(vp), n, 0)
+    assert rc == 0
+    Hm = np.triu(A, -1)
+    assert np.linalg.norm(A0 - Q @ Hm @ Q.T) / (n * np.linalg.norm(A0) * ULP) < 10
+    assert np.linalg.norm(Q.T @ Q - np.eye(n)) / (n * ULP) < 10
+
+
+def test_cfg4_full_size(gs):
+    """BASELINE config 4: one 4096x4096 Float64 matrix, Hessenberg + real Schur with Z."""
+    rng = np.random.default_rng(1234 + 4)
+    n = 4096
+    A0 = np.asfortranarray(rng.random((n, n)))
+    S = gs.gschur(A0)
+    berr, oerr = _large_checks(A0, S, n)
 
 
 def test_godunov_double_double(gs):
