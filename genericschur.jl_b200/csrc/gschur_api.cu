@@ -164,7 +164,27 @@ struct ChunkBuf {
     int32_t* dinfo = nullptr;
     uint32_t* dstats = nullptr;
     cudaStream_t stream = nullptr;
+    size_t capA = 0, capZ = 0, capw = 0, captau = 0, capn = 0, capst = 0;
 };
+
+// Per-device staging buffers and streams are cached across calls (grow-only): cudaMalloc / cudaFree of gigabytes
+// and stream creation would otherwise sit inside every end-to-end call.
+constexpr int NBUF = 4;
+struct DevicePipe {
+    ChunkBuf buf[NBUF];
+    std::mutex mu;     // one host-pointer call at a time per device
+};
+DevicePipe g_pipe[kMaxDevices];
+
+template <class P> cudaError_t grow(P*& p, size_t& cap, size_t need) {
+    if (need <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, need);
+    if (e == cudaSuccess) cap = need;
+    return e;
+}
 
 int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* err) {
 #define SL_TRY(expr)                                                                  \
@@ -181,10 +201,8 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
     const size_t es = elem_size(J.kind), ws = eig_size(J.kind);
     const size_t mat = (size_t)n * n * es;
     const int64_t count = b1 - b0;
-    constexpr int NBUF = 3;
-    ChunkBuf buf[NBUF];
-    // chunk size: aim at >= 8 chunks per slice but at least enough matrices to fill the GPU a few times over
-    int64_t chunk = (count + 7) / 8;
+    // chunk size: aim at >= 16 chunks per slice but at least enough matrices to fill the GPU a few times over
+    int64_t chunk = (count + 15) / 16;
     const int64_t min_chunk = 2048;
     if (chunk < min_chunk) chunk = min_chunk;
     if (chunk > count) chunk = count;
@@ -205,14 +223,17 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
             return rc;
         }
     }
+    DevicePipe& P = g_pipe[dev];
+    std::lock_guard<std::mutex> lk(P.mu);
+    ChunkBuf* buf = P.buf;
     for (int i = 0; i < NBUF; ++i) {
-        SL_TRY(cudaStreamCreateWithFlags(&buf[i].stream, cudaStreamNonBlocking));
-        SL_TRY(cudaMalloc(&buf[i].dA, mat * chunk));
-        if (wantZ) SL_TRY(cudaMalloc(&buf[i].dZ, mat * chunk));
-        if (!hess) SL_TRY(cudaMalloc(&buf[i].dw, ws * n * chunk));
-        if (hess) SL_TRY(cudaMalloc(&buf[i].dtau, es * (n > 1 ? n - 1 : 1) * chunk));
-        SL_TRY(cudaMalloc(&buf[i].dinfo, sizeof(int32_t) * chunk));
-        SL_TRY(cudaMalloc(&buf[i].dstats, sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX * chunk));
+        if (!buf[i].stream) SL_TRY(cudaStreamCreateWithFlags(&buf[i].stream, cudaStreamNonBlocking));
+        SL_TRY(grow(buf[i].dA, buf[i].capA, mat * chunk));
+        if (wantZ) SL_TRY(grow(buf[i].dZ, buf[i].capZ, mat * chunk));
+        if (!hess) SL_TRY(grow(buf[i].dw, buf[i].capw, ws * n * chunk));
+        if (hess) SL_TRY(grow(buf[i].dtau, buf[i].captau, es * (n > 1 ? n - 1 : 1) * chunk));
+        SL_TRY(grow(buf[i].dinfo, buf[i].capn, sizeof(int32_t) * chunk));
+        SL_TRY(grow(buf[i].dstats, buf[i].capst, sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX * chunk));
     }
     {
         int ci = 0;
@@ -277,20 +298,9 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
                                        sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX * cn, cudaMemcpyDeviceToHost, s));
         }
     }
-    for (int i = 0; i < NBUF; ++i) SL_TRY(cudaStreamSynchronize(buf[i].stream));
 cleanup:
-    for (int i = 0; i < NBUF; ++i) {
-        if (buf[i].stream) {
-            cudaStreamSynchronize(buf[i].stream);
-            cudaStreamDestroy(buf[i].stream);
-        }
-        cudaFree(buf[i].dA);
-        cudaFree(buf[i].dZ);
-        cudaFree(buf[i].dw);
-        cudaFree(buf[i].dtau);
-        cudaFree(buf[i].dinfo);
-        cudaFree(buf[i].dstats);
-    }
+    for (int i = 0; i < NBUF; ++i)
+        if (buf[i].stream) cudaStreamSynchronize(buf[i].stream);
     return rc_final;
 #undef SL_TRY
 }
