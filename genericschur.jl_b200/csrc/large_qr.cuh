@@ -13,16 +13,20 @@
 // Deflation uses the reference's test (Ahues-Tisseur with its `aa + bb`, src/GenericSchur.jl:563-600).
 #pragma once
 #include <algorithm>
+#include <chrono>
 #include <complex>
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 #include "batched.cuh"
 #include "large_gehrd.cuh"
 
 namespace gs {
 
-constexpr int LQ_NB = 8;        // bulges per chain (2 NB shifts per sweep)
-constexpr int LQ_W = 96;        // maximum window order
-constexpr int LQ_LDW = 97;      // shared-memory leading dimension (odd: conflict-free rows and columns)
+constexpr int LQ_NB = 12;       // bulges per chain (2 NB shifts per sweep)
+constexpr int LQ_W = 112;       // maximum window order (H window + U in shared memory: 2 x 112 x 113 x 8 B = 198 KB)
+constexpr int LQ_LDW = 113;     // shared-memory leading dimension (odd: conflict-free rows and columns)
+constexpr int LQ_UW = 4;        // warps that apply the reflectors to U (one row of U per lane)
 constexpr int LQ_SMALL = 128;   // active blocks up to this order go to the batched kernel
 
 struct LqScan {
@@ -76,12 +80,21 @@ __global__ void __launch_bounds__(1024) lq_scan_kernel(double* H, int n, int ien
 // Chase the chain through one window.  Bulge b at time tau sits at column p = L + tau - 4 b (1-based); it is active
 // while L <= p <= I-1.  The window is rows/columns wlo..whi of H.  U (wsz x wsz, ld LQ_W, global) receives the
 // accumulated orthogonal factor: H_window <- U' H_window U.
-__global__ void __launch_bounds__(32 * LQ_NB) lq_chase_kernel(double* H, int n, int L, int I, const double* shifts,
-                                                             int tau0, int M, int wlo, int whi, double* Uout) {
+// Warps 0..NB-1 chase one bulge each (left phase | barrier | right phase | barrier); warps NB..NB+UW-1 apply the
+// step's reflectors to U (their lanes own the rows of U) off the bulge warps' critical path, picking the
+// parameters up from a double-buffered slot in shared memory at the same two barriers.
+struct lq_refl {
+    double tau1, v1, v2;
+    int pc, nr;      // window-local column, reflector order (0 = inactive)
+};
+__global__ void __launch_bounds__(32 * (LQ_NB + LQ_UW)) lq_chase_kernel(double* H, int n, int L, int I, const double* shifts,
+                                                                       int tau0, int M, int wlo, int whi, double* Uout) {
     extern __shared__ double sm[];
     double* Hw = sm;                       // LQ_W x LQ_LDW
     double* Uw = sm + LQ_W * LQ_LDW;       // LQ_W x LQ_LDW
+    lq_refl* slots = reinterpret_cast<lq_refl*>(Uw + LQ_W * LQ_LDW);   // [2][LQ_NB]
     const int tid = threadIdx.x, lane = tid & 31, b = tid >> 5;
+    const bool is_bulge = b < LQ_NB;
     const int wsz = whi - wlo + 1;
 #define HW(i, j) Hw[((i)-wlo) + ((j)-wlo) * LQ_LDW]          // global 1-based indices
 #define UW(i, j) Uw[(i) + (j)*LQ_LDW]                        // local 0-based indices
@@ -91,68 +104,95 @@ __global__ void __launch_bounds__(32 * LQ_NB) lq_chase_kernel(double* H, int n, 
         Uw[i + j * LQ_LDW] = (i == j) ? 1.0 : 0.0;
     }
     __syncthreads();
-    const double r1r = shifts[4 * b + 0], r1i = shifts[4 * b + 1], r2r = shifts[4 * b + 2], r2i = shifts[4 * b + 3];
+    double r1r = 0, r1i = 0, r2r = 0, r2i = 0;
+    if (is_bulge) {
+        r1r = shifts[4 * b + 0];
+        r1i = shifts[4 * b + 1];
+        r2r = shifts[4 * b + 2];
+        r2i = shifts[4 * b + 3];
+    }
     for (int tau = tau0; tau < tau0 + M; ++tau) {
-        const int p = L + tau - 4 * b;
-        const bool active = (p >= L && p <= I - 1);
-        const int nr = (I - p + 1 < 3) ? I - p + 1 : 3;
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0, tau1 = 0.0;
-        if (active) {
-            if (p == L) {
-                // first column of (H - s1)(H - s2), src/GenericSchur.jl:855-863
-                const double hmm = HW(L, L);
-                double H21s = HW(L + 1, L);
-                double s = fabs(hmm - r2r) + fabs(r2i) + fabs(H21s);
-                H21s = H21s / s;
-                v0 = H21s * HW(L, L + 1) + (hmm - r1r) * ((hmm - r2r) / s) - r1i * (r2i / s);
-                v1 = H21s * (hmm + HW(L + 1, L + 1) - r1r - r2r);
-                v2 = (nr == 3) ? H21s * HW(L + 2, L + 1) : 0.0;
-                s = fabs(v0) + fabs(v1) + fabs(v2);
-                v0 /= s;
-                v1 /= s;
-                v2 /= s;
-            } else {
-                v0 = HW(p, p - 1);
-                v1 = HW(p + 1, p - 1);
-                v2 = (nr == 3) ? HW(p + 2, p - 1) : 0.0;
+        lq_refl* slot = slots + (tau & 1) * LQ_NB;
+        int p = 0, nr = 0;
+        bool active = false;
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, tau1 = 0.0, tau2 = 0.0, tau3 = 0.0;
+        if (is_bulge) {
+            p = L + tau - 4 * b;
+            active = (p >= L && p <= I - 1);
+            nr = (I - p + 1 < 3) ? I - p + 1 : 3;
+            if (active) {
+                if (p == L) {
+                    // first column of (H - s1)(H - s2), src/GenericSchur.jl:855-863
+                    const double hmm = HW(L, L);
+                    double H21s = HW(L + 1, L);
+                    double s = fabs(hmm - r2r) + fabs(r2i) + fabs(H21s);
+                    H21s = H21s / s;
+                    v0 = H21s * HW(L, L + 1) + (hmm - r1r) * ((hmm - r2r) / s) - r1i * (r2i / s);
+                    v1 = H21s * (hmm + HW(L + 1, L + 1) - r1r - r2r);
+                    v2 = (nr == 3) ? H21s * HW(L + 2, L + 1) : 0.0;
+                    s = fabs(v0) + fabs(v1) + fabs(v2);
+                    v0 /= s;
+                    v1 /= s;
+                    v2 /= s;
+                } else {
+                    v0 = HW(p, p - 1);
+                    v1 = HW(p + 1, p - 1);
+                    v2 = (nr == 3) ? HW(p + 2, p - 1) : 0.0;
+                }
+                tau1 = reflector_real_small(v0, v1, v2, nr);
+                tau2 = tau1 * v1;
+                tau3 = tau1 * v2;
+                // ---- left phase: rows p..p+nr-1, columns p..whi (disjoint rows across bulges) ----
+                for (int j = p + lane; j <= whi; j += 32) {
+                    const double a = HW(p, j), bb = HW(p + 1, j), c = (nr == 3) ? HW(p + 2, j) : 0.0;
+                    const double ss = a + v1 * bb + v2 * c;
+                    HW(p, j) = a - ss * tau1;
+                    HW(p + 1, j) = bb - ss * tau2;
+                    if (nr == 3) HW(p + 2, j) = c - ss * tau3;
+                }
+                if (lane == 0 && p > L) {
+                    HW(p, p - 1) = v0;
+                    HW(p + 1, p - 1) = 0.0;
+                    if (nr == 3) HW(p + 2, p - 1) = 0.0;
+                }
             }
-            tau1 = reflector_real_small(v0, v1, v2, nr);
+            if (lane == 0) {
+                slot[b].tau1 = tau1;
+                slot[b].v1 = v1;
+                slot[b].v2 = v2;
+                slot[b].pc = p - wlo;
+                slot[b].nr = active ? nr : 0;
+            }
         }
         __syncthreads();
-        const double tau2 = tau1 * v1, tau3 = tau1 * v2;
-        // ---- left phase: rows p..p+nr-1, columns p..whi (disjoint rows across bulges) ----
-        if (active) {
-            for (int j = p + lane; j <= whi; j += 32) {
-                const double a = HW(p, j), bb = HW(p + 1, j), c = (nr == 3) ? HW(p + 2, j) : 0.0;
-                const double ss = a + v1 * bb + v2 * c;
-                HW(p, j) = a - ss * tau1;
-                HW(p + 1, j) = bb - ss * tau2;
-                if (nr == 3) HW(p + 2, j) = c - ss * tau3;
+        if (is_bulge) {
+            // ---- right phase: columns p..p+nr-1, rows wlo..min(p+3, I) (disjoint columns across bulges) ----
+            if (active) {
+                const int rmax = (p + 3 < I) ? p + 3 : I;
+                for (int r = wlo + lane; r <= rmax; r += 32) {
+                    const double a = HW(r, p), bb = HW(r, p + 1), c = (nr == 3) ? HW(r, p + 2) : 0.0;
+                    const double ss = a + v1 * bb + v2 * c;
+                    HW(r, p) = a - ss * tau1;
+                    HW(r, p + 1) = bb - ss * tau2;
+                    if (nr == 3) HW(r, p + 2) = c - ss * tau3;
+                }
             }
-            if (lane == 0 && p > L) {
-                HW(p, p - 1) = v0;
-                HW(p + 1, p - 1) = 0.0;
-                if (nr == 3) HW(p + 2, p - 1) = 0.0;
-            }
-        }
-        __syncthreads();
-        // ---- right phase: columns p..p+nr-1, rows wlo..min(p+3, I) (disjoint columns across bulges), and U ----
-        if (active) {
-            const int rmax = (p + 3 < I) ? p + 3 : I;
-            for (int r = wlo + lane; r <= rmax; r += 32) {
-                const double a = HW(r, p), bb = HW(r, p + 1), c = (nr == 3) ? HW(r, p + 2) : 0.0;
-                const double ss = a + v1 * bb + v2 * c;
-                HW(r, p) = a - ss * tau1;
-                HW(r, p + 1) = bb - ss * tau2;
-                if (nr == 3) HW(r, p + 2) = c - ss * tau3;
-            }
-            const int pc = p - wlo;
-            for (int r = lane; r < wsz; r += 32) {
-                const double a = UW(r, pc), bb = UW(r, pc + 1), c = (nr == 3) ? UW(r, pc + 2) : 0.0;
-                const double ss = a + v1 * bb + v2 * c;
-                UW(r, pc) = a - ss * tau1;
-                UW(r, pc + 1) = bb - ss * tau2;
-                if (nr == 3) UW(r, pc + 2) = c - ss * tau3;
+        } else {
+            // ---- U <- U G for every reflector of this step (disjoint columns: any order) ----
+            const int r = (b - LQ_NB) * 32 + lane;
+            if (r < wsz) {
+#pragma unroll 4
+                for (int q = 0; q < LQ_NB; ++q) {
+                    const int rn = slot[q].nr;
+                    if (rn == 0) continue;
+                    const int pc = slot[q].pc;
+                    const double t1 = slot[q].tau1, w1 = slot[q].v1, w2 = slot[q].v2;
+                    const double a = UW(r, pc), bb = UW(r, pc + 1), c = (rn == 3) ? UW(r, pc + 2) : 0.0;
+                    const double ss = a + w1 * bb + w2 * c;
+                    UW(r, pc) = a - ss * t1;
+                    UW(r, pc + 1) = bb - ss * (t1 * w1);
+                    if (rn == 3) UW(r, pc + 2) = c - ss * (t1 * w2);
+                }
             }
         }
         __syncthreads();
@@ -209,13 +249,15 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
     const size_t wbuf = (size_t)LQ_SMALL * std::max(n, LQ_SMALL);
     double* base = nullptr;
     // scratch: U (LQ_SMALL^2), tmp (LQ_SMALL x n), blk (LQ_SMALL^2), zblk (LQ_SMALL^2), wblk, shifts, scan
-    const size_t total = 3 * (size_t)LQ_SMALL * LQ_SMALL + wbuf + 2 * LQ_SMALL + 4 * LQ_NB + 64;
+    const size_t total = 5 * (size_t)LQ_SMALL * LQ_SMALL + wbuf + 2 * LQ_SMALL + 4 * LQ_NB + 64;
     LG_TRY(cudaMallocAsync((void**)&base, total * sizeof(double), s));
     double* dU = base;
     double* dBlk = dU + (size_t)LQ_SMALL * LQ_SMALL;
     double* dZb = dBlk + (size_t)LQ_SMALL * LQ_SMALL;
     double* dTmp = dZb + (size_t)LQ_SMALL * LQ_SMALL;
-    double* dWb = dTmp + wbuf;
+    double* dU1 = dTmp + wbuf;                               // second U buffer (windows alternate)
+    double* dTmpA = dU1 + (size_t)LQ_SMALL * LQ_SMALL;       // scratch of the near-window GEMM (stream A)
+    double* dWb = dTmpA + (size_t)LQ_SMALL * LQ_SMALL;
     double* dShift = dWb + 2 * LQ_SMALL;
     LqScan* dScan = reinterpret_cast<LqScan*>(dShift + 4 * LQ_NB);
     int* dInfo = reinterpret_cast<int*>(dScan + 1);
@@ -223,8 +265,15 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t chase_smem = 2 * (size_t)LQ_W * LQ_LDW * sizeof(double);
+    const size_t chase_smem = 2 * (size_t)LQ_W * LQ_LDW * sizeof(double) + 2 * LQ_NB * sizeof(lq_refl) + 16;
     LG_TRY(cudaFuncSetAttribute(lq_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chase_smem));
+    // every kernel of the QR pipeline asks for the same (maximum) shared-memory carve-out: the chase kernel needs
+    // 198 KB, and an SM whose L1/shared split has to be reconfigured between kernels must drain first
+    cudaFuncSetAttribute(dgemm_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(dgemm_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(dgemm_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(lq_copy_block_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(lq_chase_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 
     auto run_small = [&](double* blk, int m, double* zb, double* wb, bool wantz) -> int {
         // batched kernel on one m x m Hessenberg block: blk <- T, zb <- Z_blk (in: identity), wb <- eigenvalues
@@ -253,37 +302,75 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
         if (rc) *err = e2;
         return rc;
     };
-    // apply an orthogonal m x m factor Q (ld ldq) that transformed rows/cols lo..hi (1-based):
-    //   H[lo:hi, hi+1:n] <- Q' H[...],  H[1:lo-1, lo:hi] <- H[...] Q,  Z[:, lo:hi] <- Z[...] Q
-    auto apply_outside = [&](const double* Q, int ldq, int lo, int hi) -> int {
-        const int m = hi - lo + 1;
-        const int nr = n - hi;
-        if (nr > 0) {
-            double* C = H + (size_t)(lo - 1) + (size_t)hi * n;
-            LG_TRY(dgemm(s, true, false, m, nr, m, 1.0, Q, ldq, C, n, 0.0, dTmp, m));
-            lq_copy(s, dTmp, m, C, n, m, nr);
-        }
-        const int nt = lo - 1;
-        if (nt > 0) {
-            double* C = H + (size_t)(lo - 1) * n;
-            LG_TRY(dgemm(s, false, false, nt, m, m, 1.0, C, n, Q, ldq, 0.0, dTmp, nt));
-            lq_copy(s, dTmp, nt, C, n, nt, m);
-        }
-        if (Z) {
-            double* C = Z + (size_t)(lo - 1) * n;
-            LG_TRY(dgemm(s, false, false, n, m, m, 1.0, C, n, Q, ldq, 0.0, dTmp, n));
-            lq_copy(s, dTmp, n, C, n, n, m);
-        }
+    // pieces of "apply the orthogonal m x m factor Q (ld ldq) that transformed rows/cols lo..hi (1-based)":
+    //   left : H[lo:hi, c0:c1] <- Q' H[lo:hi, c0:c1]      top : H[1:lo-1, lo:hi] <- H[...] Q      zz : Z[:, lo:hi] <- Z[...] Q
+    auto left_part = [&](cudaStream_t st, const double* Q, int ldq, int lo, int hi, int c0, int c1, double* tmp) -> int {
+        const int m = hi - lo + 1, nc = c1 - c0 + 1;
+        if (nc <= 0) return 0;
+        double* C = H + (size_t)(lo - 1) + (size_t)(c0 - 1) * n;
+        LG_TRY(dgemm(st, true, false, m, nc, m, 1.0, Q, ldq, C, n, 0.0, tmp, m));
+        lq_copy(st, tmp, m, C, n, m, nc);
         return 0;
     };
+    auto top_part = [&](cudaStream_t st, const double* Q, int ldq, int lo, int hi, double* tmp) -> int {
+        const int m = hi - lo + 1, nt = lo - 1;
+        if (nt <= 0) return 0;
+        double* C = H + (size_t)(lo - 1) * n;
+        LG_TRY(dgemm(st, false, false, nt, m, m, 1.0, C, n, Q, ldq, 0.0, tmp, nt));
+        lq_copy(st, tmp, nt, C, n, nt, m);
+        return 0;
+    };
+    auto z_part = [&](cudaStream_t st, const double* Q, int ldq, int lo, int hi, double* tmp) -> int {
+        const int m = hi - lo + 1;
+        if (!Z) return 0;
+        double* C = Z + (size_t)(lo - 1) * n;
+        LG_TRY(dgemm(st, false, false, n, m, m, 1.0, C, n, Q, ldq, 0.0, tmp, n));
+        lq_copy(st, tmp, n, C, n, n, m);
+        return 0;
+    };
+    auto apply_outside = [&](const double* Q, int ldq, int lo, int hi) -> int {
+        int rc = left_part(s, Q, ldq, lo, hi, hi + 1, n, dTmp);
+        if (rc == 0) rc = top_part(s, Q, ldq, lo, hi, dTmp);
+        if (rc == 0) rc = z_part(s, Q, ldq, lo, hi, dTmp);
+        return rc;
+    };
+    // second stream: the far updates of window t run while window t+1 is being chased
+    // The chase kernel needs a whole SM (198 KB of shared memory): its stream gets the highest priority so that the
+    // block scheduler hands it the first SM the concurrently running GEMMs vacate.
+    cudaStream_t sB = nullptr, sA = nullptr;
+    cudaEvent_t evChase[2] = {nullptr, nullptr}, evFar[2] = {nullptr, nullptr};
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    LG_TRY(cudaStreamCreateWithPriority(&sB, cudaStreamNonBlocking, prio_lo));
+    LG_TRY(cudaStreamCreateWithPriority(&sA, cudaStreamNonBlocking, prio_hi));
+    LG_TRY(cudaStreamSynchronize(s));      // everything before this call has completed; from here on sA replaces s
+    cudaStream_t s_caller = s;
+    s = sA;
+    for (int q = 0; q < 2; ++q) {
+        LG_TRY(cudaEventCreateWithFlags(&evChase[q], cudaEventDisableTiming));
+        LG_TRY(cudaEventCreateWithFlags(&evFar[q], cudaEventDisableTiming));
+    }
+    struct Win {
+        int tau0, M, wlo, whi;
+    };
+    std::vector<Win> wins;
 
+    const bool dbg_time = std::getenv("GSCHUR_LQ_TIMING") != nullptr;
+    double t_scan = 0, t_small = 0, t_shift = 0, t_enq = 0;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     int iend = n;
     long sweeps_total = 0;
     int since_deflation = 0;
-    const long maxsweeps = 30L * n + 100;
+    long maxsweeps = 30L * n + 100;
+    // development knobs (timing experiments only): cap the number of sweeps / skip one side of the pipeline
+    const char* dbg_ms = std::getenv("GSCHUR_LQ_MAXSWEEPS");
+    if (dbg_ms) maxsweeps = std::atol(dbg_ms);
+    const char* dbg_skip = std::getenv("GSCHUR_LQ_SKIP");
+    const int skip = dbg_skip ? std::atoi(dbg_skip) : 0;
     std::vector<double> hshift(2 * 2 * LQ_NB), hpairs(4 * LQ_NB);
     int rc_final = 0;
     while (iend >= 1) {
+        double t0 = now();
         lq_scan_kernel<<<1, 1024, 0, s>>>(H, n, iend, dScan);
         note_launch();
         LqScan hs;
@@ -291,6 +378,8 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
         LG_TRY(cudaStreamSynchronize(s));
         const int istart = hs.istart;
         const int nw = iend - istart + 1;
+        t_scan += now() - t0;
+        t0 = now();
         if (nw <= LQ_SMALL) {
             // finish the block with the batched kernel, back-transform with GEMMs
             lq_copy(s, H + (size_t)(istart - 1) + (size_t)(istart - 1) * n, n, dBlk, nw, nw, nw);
@@ -308,6 +397,7 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
                 if (rc) { cudaFreeAsync(base, s); return rc; }
             }
             if (stats) stats->small_blocks += 1;
+            t_small += now() - t0;
             iend = istart - 1;
             since_deflation = 0;
             continue;
@@ -362,11 +452,13 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
             }
         }
         LG_TRY(cudaMemcpyAsync(dShift, hpairs.data(), sizeof(double) * 4 * LQ_NB, cudaMemcpyHostToDevice, s));
+        t_shift += now() - t0;
+        t0 = now();
         // ---- chase the chain from the top (L = istart) to the bottom (I = iend) ----
         const int L = istart, I = iend;
         const int tau_end = (I - 1 - L) + 4 * (LQ_NB - 1);        // last time step with an active bulge
-        int tau0 = 0;
-        while (tau0 <= tau_end) {
+        wins.clear();
+        for (int tau0 = 0; tau0 <= tau_end;) {
             // window for M steps: from the trailing active bulge's column - 1 to the leading active bulge's end + 3
             int M = LQ_W - (4 * (LQ_NB - 1) + 6);
             if (tau0 + M - 1 > tau_end) M = tau_end - tau0 + 1;
@@ -377,24 +469,57 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
                 pmin = std::min(pmin, std::max(p0, L));
                 pmax = std::max(pmax, std::min(p1, I - 1));
             }
-            if (pmax < 0) { tau0 += M; continue; }
-            const int wlo = std::max(L, pmin - 1), whi = std::min(I, pmax + 3);
-            const int wsz = whi - wlo + 1;
-            if (wsz > LQ_W) { *err = "internal: chase window too large"; cudaFreeAsync(base, s); return -2; }
-            lq_chase_kernel<<<1, 32 * LQ_NB, chase_smem, s>>>(H, n, L, I, dShift, tau0, M, wlo, whi, dU);
-            note_launch();
-            int rc = apply_outside(dU, LQ_W, wlo, whi);
-            if (rc) { cudaFreeAsync(base, s); return rc; }
-            if (stats) stats->windows += 1;
+            if (pmax >= 0) {
+                Win wn{tau0, M, std::max(L, pmin - 1), std::min(I, pmax + 3)};
+                if (wn.whi - wn.wlo + 1 > LQ_W) { *err = "internal: chase window too large"; cudaFreeAsync(base, s); return -2; }
+                wins.push_back(wn);
+            }
             tau0 += M;
         }
+        const int nwin = (int)wins.size();
+        for (int t = 0; t < nwin; ++t) {
+            const Win& wn = wins[t];
+            double* U = (t & 1) ? dU1 : dU;
+            // stream A: chase, then the near columns the next window is going to need
+            if (!(skip & 2)) {
+                lq_chase_kernel<<<1, 32 * (LQ_NB + LQ_UW), chase_smem, s>>>(H, n, L, I, dShift, wn.tau0, wn.M, wn.wlo, wn.whi, U);
+                note_launch();
+            }
+            LG_TRY(cudaEventRecord(evChase[t & 1], s));
+            const int nearhi = (t + 1 < nwin) ? std::min(n, std::max(wn.whi, wins[t + 1].whi)) : wn.whi;
+            if (t >= 1) LG_TRY(cudaStreamWaitEvent(s, evFar[(t - 1) & 1], 0));
+            int rc = left_part(s, U, LQ_W, wn.wlo, wn.whi, wn.whi + 1, nearhi, dTmpA);
+            if (rc) { cudaFreeAsync(base, s); return rc; }
+            // stream B: everything else outside the window
+            LG_TRY(cudaStreamWaitEvent(sB, evChase[t & 1], 0));
+            if (!(skip & 1)) {
+                rc = left_part(sB, U, LQ_W, wn.wlo, wn.whi, nearhi + 1, n, dTmp);
+                if (rc == 0) rc = top_part(sB, U, LQ_W, wn.wlo, wn.whi, dTmp);
+                if (rc == 0) rc = z_part(sB, U, LQ_W, wn.wlo, wn.whi, dTmp);
+            }
+            if (rc) { cudaFreeAsync(base, s); return rc; }
+            LG_TRY(cudaEventRecord(evFar[t & 1], sB));
+            if (stats) stats->windows += 1;
+        }
+        if (nwin > 0) LG_TRY(cudaStreamWaitEvent(s, evFar[(nwin - 1) & 1], 0));
+        if (nwin > 1) LG_TRY(cudaStreamWaitEvent(s, evFar[(nwin - 2) & 1], 0));
+        t_enq += now() - t0;
         if (stats) stats->sweeps += 1;
     }
     if (rc_final == 0 && w) {
         lq_eigs_kernel<<<(n + 255) / 256, 256, 0, s>>>(H, n, w);
         note_launch();
     }
+    if (dbg_time) fprintf(stderr, "[lg_qr] scan+sync %.3f s, small blocks %.3f s, shifts %.3f s, window enqueue %.3f s\n", t_scan, t_small, t_shift, t_enq);
     LG_TRY(cudaStreamSynchronize(s));
+    cudaStreamSynchronize(sB);
+    cudaStreamDestroy(sB);
+    cudaStreamDestroy(sA);
+    s = s_caller;
+    for (int q = 0; q < 2; ++q) {
+        cudaEventDestroy(evChase[q]);
+        cudaEventDestroy(evFar[q]);
+    }
     cudaFreeAsync(base, s);
     return rc_final;
 }
