@@ -172,6 +172,10 @@ struct ChunkBuf {
 constexpr int NBUF = 4;
 struct DevicePipe {
     ChunkBuf buf[NBUF];
+    // pinned staging for the small outputs (w, info, stats, tau) of a whole slice: a D2H copy into the caller's
+    // pageable arrays would block the enqueue loop until the chunk's kernels finish and serialise the pipeline
+    char* hstage = nullptr;
+    size_t hcap = 0;
     std::mutex mu;     // one host-pointer call at a time per device
 };
 DevicePipe g_pipe[kMaxDevices];
@@ -226,6 +230,22 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
     DevicePipe& P = g_pipe[dev];
     std::lock_guard<std::mutex> lk(P.mu);
     ChunkBuf* buf = P.buf;
+    const size_t tau_per = es * (size_t)(n > 1 ? n - 1 : 0);
+    const size_t off_w = 0;
+    const size_t off_info = off_w + (hess ? tau_per : ws * n) * (size_t)count;
+    const size_t off_stats = off_info + sizeof(int32_t) * (size_t)count;
+    const size_t stage_bytes = off_stats + sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX * (size_t)count;
+    if (stage_bytes > P.hcap) {
+        if (P.hstage) cudaFreeHost(P.hstage);
+        P.hstage = nullptr;
+        P.hcap = 0;
+        if (cudaMallocHost((void**)&P.hstage, stage_bytes) != cudaSuccess) {
+            *err = "cudaMallocHost(staging) failed";
+            return GSCHUR_ERR_CUDA;
+        }
+        P.hcap = stage_bytes;
+    }
+    char* hst = P.hstage;
     for (int i = 0; i < NBUF; ++i) {
         if (!buf[i].stream) SL_TRY(cudaStreamCreateWithFlags(&buf[i].stream, cudaStreamNonBlocking));
         SL_TRY(grow(buf[i].dA, buf[i].capA, mat * chunk));
@@ -286,21 +306,30 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
                                                  cudaMemcpyDeviceToHost, s));
                 }
             }
+            const size_t l0 = (size_t)(c0 - b0);     // index within the slice
             if (!hess)
-                SL_TRY(cudaMemcpyAsync(J.w + (size_t)c0 * n * ws, B.dw, ws * n * cn, cudaMemcpyDeviceToHost, s));
+                SL_TRY(cudaMemcpyAsync(hst + off_w + l0 * n * ws, B.dw, ws * n * cn, cudaMemcpyDeviceToHost, s));
             if (hess && n > 1)
-                SL_TRY(cudaMemcpyAsync(J.tau + (size_t)c0 * (n - 1) * es, B.dtau, es * (n - 1) * cn,
-                                       cudaMemcpyDeviceToHost, s));
+                SL_TRY(cudaMemcpyAsync(hst + off_w + l0 * tau_per, B.dtau, tau_per * cn, cudaMemcpyDeviceToHost, s));
             if (J.info && !hess)
-                SL_TRY(cudaMemcpyAsync(J.info + c0, B.dinfo, sizeof(int32_t) * cn, cudaMemcpyDeviceToHost, s));
+                SL_TRY(cudaMemcpyAsync(hst + off_info + l0 * sizeof(int32_t), B.dinfo, sizeof(int32_t) * cn,
+                                       cudaMemcpyDeviceToHost, s));
             if (J.stats && !hess)
-                SL_TRY(cudaMemcpyAsync(J.stats + (size_t)c0 * GSCHUR_STATS_PER_MATRIX, B.dstats,
+                SL_TRY(cudaMemcpyAsync(hst + off_stats + l0 * sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX, B.dstats,
                                        sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX * cn, cudaMemcpyDeviceToHost, s));
         }
     }
 cleanup:
     for (int i = 0; i < NBUF; ++i)
         if (buf[i].stream) cudaStreamSynchronize(buf[i].stream);
+    if (rc_final == 0) {
+        if (!hess) std::memcpy(J.w + (size_t)b0 * n * ws, hst + off_w, ws * n * (size_t)count);
+        if (hess && n > 1) std::memcpy(J.tau + (size_t)b0 * tau_per, hst + off_w, tau_per * (size_t)count);
+        if (J.info && !hess) std::memcpy(J.info + b0, hst + off_info, sizeof(int32_t) * (size_t)count);
+        if (J.stats && !hess)
+            std::memcpy(J.stats + (size_t)b0 * GSCHUR_STATS_PER_MATRIX, hst + off_stats,
+                        sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX * (size_t)count);
+    }
     return rc_final;
 #undef SL_TRY
 }
