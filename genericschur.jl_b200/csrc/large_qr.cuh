@@ -27,6 +27,8 @@ constexpr int LQ_NB = 12;       // bulges per chain (2 NB shifts per sweep)
 constexpr int LQ_W = 112;       // maximum window order (H window + U in shared memory: 2 x 112 x 113 x 8 B = 198 KB)
 constexpr int LQ_LDW = 113;     // shared-memory leading dimension (odd: conflict-free rows and columns)
 constexpr int LQ_UW = 4;        // warps that apply the reflectors to U (one row of U per lane)
+constexpr int LQ_MAXC = 4;      // chains of NB bulges in flight per sweep (each on its own SM)
+constexpr int LQ_DELTA = 192;   // column distance between consecutive chains (>= window + steps per window)
 constexpr int LQ_SMALL = 128;   // active blocks up to this order go to the batched kernel
 
 struct LqScan {
@@ -87,8 +89,18 @@ struct lq_refl {
     double tau1, v1, v2;
     int pc, nr;      // window-local column, reflector order (0 = inactive)
 };
-__global__ void __launch_bounds__(32 * (LQ_NB + LQ_UW)) lq_chase_kernel(double* H, int n, int L, int I, const double* shifts,
-                                                                       int tau0, int M, int wlo, int whi, double* Uout) {
+struct LqChaseArgs {
+    int wlo[LQ_MAXC], whi[LQ_MAXC];     // window of each chain (whi < wlo: chain inactive in this time block)
+    double* U[LQ_MAXC];
+};
+__global__ void __launch_bounds__(32 * (LQ_NB + LQ_UW)) lq_chase_kernel(double* H, int n, int L, int I, const double* shifts_all,
+                                                                       int tau0_all, int M, LqChaseArgs args) {
+    const int chain = blockIdx.x;
+    const int wlo = args.wlo[chain], whi = args.whi[chain];
+    if (whi < wlo) return;
+    double* Uout = args.U[chain];
+    const double* shifts = shifts_all + 4 * LQ_NB * chain;
+    const int tau0 = tau0_all - LQ_DELTA * chain;     // chain c runs LQ_DELTA columns behind chain c-1
     extern __shared__ double sm[];
     double* Hw = sm;                       // LQ_W x LQ_LDW
     double* Uw = sm + LQ_W * LQ_LDW;       // LQ_W x LQ_LDW
@@ -206,6 +218,97 @@ __global__ void __launch_bounds__(32 * (LQ_NB + LQ_UW)) lq_chase_kernel(double* 
 #undef UW
 }
 
+// One launch applies the accumulated factors of all chains of a time block to everything outside their windows,
+// in place, on the FP64 tensor cores:
+//   left  strips: H[wlo:whi, c0:c0+63] <- U' * H[...]         (64 columns per CTA)
+//   right strips: H[r0:r0+63, wlo:whi] <- H[...] * U  (rows above the window),  Z[r0:r0+63, wlo:whi] <- Z[...] * U
+// A CTA stages U (<= 112 x 112) and its strip in shared memory (leading dimensions = 4 mod 16: the DMMA fragment
+// loads are conflict-free), so the update is safe in place, then each of its 8 warps owns 8 columns (left) or
+// 8 rows (right) of the strip: 14 m8n8 accumulator tiles per warp.
+constexpr int LQ_LDU = 116, LQ_LDT_L = 116, LQ_LDT_R = 68;
+struct LqApplyArgs {
+    int C, mode;                         // mode bits: 1 = left strips, 2 = right strips of H (top), 4 = right strips of Z
+    int wlo[LQ_MAXC], wsz[LQ_MAXC];      // wsz <= 0: chain inactive
+    int lc0[LQ_MAXC], lc1[LQ_MAXC];      // left strips cover columns lc0..lc1 (1-based, inclusive)
+    const double* U[LQ_MAXC];
+};
+__host__ __device__ inline int lq_strips(int count) { return count > 0 ? (count + 63) / 64 : 0; }
+
+__global__ void __launch_bounds__(256) lq_apply_kernel(double* H, double* Z, int n, LqApplyArgs a) {
+    extern __shared__ double sm[];
+    double* Us = sm;                              // [k + m * LQ_LDU]
+    double* Ts = sm + LQ_W * LQ_LDU;              // strip tile
+    // ---- decode blockIdx -> (chain, type, strip) ----
+    int rem = blockIdx.x, chain = -1, type = -1, strip = 0;
+    for (int c = 0; c < a.C && chain < 0; ++c) {
+        if (a.wsz[c] <= 0) continue;
+        const int nl = (a.mode & 1) ? lq_strips(a.lc1[c] - a.lc0[c] + 1) : 0;
+        const int nt = (a.mode & 2) ? lq_strips(a.wlo[c] - 1) : 0;
+        const int nz = ((a.mode & 4) && Z) ? lq_strips(n) : 0;
+        if (rem < nl) { chain = c; type = 0; strip = rem; }
+        else if (rem < nl + nt) { chain = c; type = 1; strip = rem - nl; }
+        else if (rem < nl + nt + nz) { chain = c; type = 2; strip = rem - nl - nt; }
+        else rem -= nl + nt + nz;
+    }
+    if (chain < 0) return;
+    const int wlo = a.wlo[chain], wsz = a.wsz[chain];
+    const double* U = a.U[chain];
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    const int K = (wsz + 3) & ~3;
+    for (int e = tid; e < LQ_W * LQ_W; e += 256) {
+        const int i = e % LQ_W, j = e / LQ_W;
+        Us[i + j * LQ_LDU] = (i < wsz && j < wsz) ? U[i + j * LQ_W] : 0.0;
+    }
+    double acc[14][2];
+#pragma unroll
+    for (int t = 0; t < 14; ++t) acc[t][0] = acc[t][1] = 0.0;
+    if (type == 0) {
+        const int c0 = a.lc0[chain] + 64 * strip;                       // 1-based first column
+        const int cnt = min(64, a.lc1[chain] - c0 + 1);
+        double* C = H + (size_t)(wlo - 1) + (size_t)(c0 - 1) * n;
+        for (int e = tid; e < LQ_W * 64; e += 256) {
+            const int i = e % LQ_W, j = e / LQ_W;
+            Ts[i + j * LQ_LDT_L] = (i < wsz && j < cnt) ? C[(size_t)i + (size_t)j * n] : 0.0;
+        }
+        __syncthreads();
+        for (int k = 0; k < K; k += 4) {
+            const double b = Ts[(k + tig) + (w * 8 + gid) * LQ_LDT_L];
+#pragma unroll
+            for (int mt = 0; mt < 14; ++mt) dmma8x8x4(acc[mt][0], acc[mt][1], Us[(k + tig) + (mt * 8 + gid) * LQ_LDU], b);
+        }
+#pragma unroll
+        for (int mt = 0; mt < 14; ++mt)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int row = mt * 8 + gid, col = w * 8 + 2 * tig + q;
+                if (row < wsz && col < cnt) C[(size_t)row + (size_t)col * n] = acc[mt][q];
+            }
+    } else {
+        double* base = (type == 1) ? H : Z;
+        const int rows_total = (type == 1) ? wlo - 1 : n;
+        const int r0 = 64 * strip;                                      // 0-based first row
+        const int cnt = min(64, rows_total - r0);
+        double* C = base + (size_t)r0 + (size_t)(wlo - 1) * n;
+        for (int e = tid; e < 64 * LQ_W; e += 256) {
+            const int i = e % 64, j = e / 64;
+            Ts[i + j * LQ_LDT_R] = (i < cnt && j < wsz) ? C[(size_t)i + (size_t)j * n] : 0.0;
+        }
+        __syncthreads();
+        for (int k = 0; k < K; k += 4) {
+            const double av = Ts[(w * 8 + gid) + (k + tig) * LQ_LDT_R];
+#pragma unroll
+            for (int nt = 0; nt < 14; ++nt) dmma8x8x4(acc[nt][0], acc[nt][1], av, Us[(k + tig) + (nt * 8 + gid) * LQ_LDU]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 14; ++nt)
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int row = w * 8 + gid, col = nt * 8 + 2 * tig + q;
+                if (row < cnt && col < wsz) C[(size_t)row + (size_t)col * n] = acc[nt][q];
+            }
+    }
+}
+
 __global__ void lq_copy_block_kernel(const double* src, int lds, double* dst, int ldd, int rows, int cols) {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx < (size_t)rows * cols) {
@@ -249,7 +352,8 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
     const size_t wbuf = (size_t)LQ_SMALL * std::max(n, LQ_SMALL);
     double* base = nullptr;
     // scratch: U (LQ_SMALL^2), tmp (LQ_SMALL x n), blk (LQ_SMALL^2), zblk (LQ_SMALL^2), wblk, shifts, scan
-    const size_t total = 5 * (size_t)LQ_SMALL * LQ_SMALL + wbuf + 2 * LQ_SMALL + 4 * LQ_NB + 64;
+    const size_t total = 5 * (size_t)LQ_SMALL * LQ_SMALL + wbuf + 2 * LQ_SMALL + 4 * LQ_NB * LQ_MAXC + 64 +
+                         2 * (size_t)LQ_MAXC * LQ_W * LQ_W;
     LG_TRY(cudaMallocAsync((void**)&base, total * sizeof(double), s));
     double* dU = base;
     double* dBlk = dU + (size_t)LQ_SMALL * LQ_SMALL;
@@ -259,7 +363,8 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
     double* dTmpA = dU1 + (size_t)LQ_SMALL * LQ_SMALL;       // scratch of the near-window GEMM (stream A)
     double* dWb = dTmpA + (size_t)LQ_SMALL * LQ_SMALL;
     double* dShift = dWb + 2 * LQ_SMALL;
-    LqScan* dScan = reinterpret_cast<LqScan*>(dShift + 4 * LQ_NB);
+    double* dUall = dShift + 4 * LQ_NB * LQ_MAXC;            // [2 parities][LQ_MAXC chains][LQ_W x LQ_W]
+    LqScan* dScan = reinterpret_cast<LqScan*>(dUall + 2 * (size_t)LQ_MAXC * LQ_W * LQ_W);
     int* dInfo = reinterpret_cast<int*>(dScan + 1);
     unsigned long long* dCounter = reinterpret_cast<unsigned long long*>(dScan + 4);
     int dev = 0, sms = 148;
@@ -267,6 +372,9 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const size_t chase_smem = 2 * (size_t)LQ_W * LQ_LDW * sizeof(double) + 2 * LQ_NB * sizeof(lq_refl) + 16;
     LG_TRY(cudaFuncSetAttribute(lq_chase_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)chase_smem));
+    const size_t apply_smem = ((size_t)LQ_W * LQ_LDU + std::max(LQ_LDT_L * 64, LQ_LDT_R * LQ_W)) * sizeof(double);
+    LG_TRY(cudaFuncSetAttribute(lq_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)apply_smem));
+    cudaFuncSetAttribute(lq_apply_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // every kernel of the QR pipeline asks for the same (maximum) shared-memory carve-out: the chase kernel needs
     // 198 KB, and an SM whose L1/shared split has to be reconfigured between kernels must drain first
     cudaFuncSetAttribute(dgemm_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -351,7 +459,8 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
         LG_TRY(cudaEventCreateWithFlags(&evFar[q], cudaEventDisableTiming));
     }
     struct Win {
-        int tau0, M, wlo, whi;
+        int tau0, M;
+        int wlo[LQ_MAXC], whi[LQ_MAXC];
     };
     std::vector<Win> wins;
 
@@ -367,7 +476,7 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
     if (dbg_ms) maxsweeps = std::atol(dbg_ms);
     const char* dbg_skip = std::getenv("GSCHUR_LQ_SKIP");
     const int skip = dbg_skip ? std::atoi(dbg_skip) : 0;
-    std::vector<double> hshift(2 * 2 * LQ_NB), hpairs(4 * LQ_NB);
+    std::vector<double> hshift(2 * 2 * LQ_NB * LQ_MAXC), hpairs(4 * LQ_NB * LQ_MAXC);
     int rc_final = 0;
     while (iend >= 1) {
         double t0 = now();
@@ -404,8 +513,13 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
         }
         if (++sweeps_total > maxsweeps) { rc_final = iend; break; }
         since_deflation += 1;
-        // ---- shifts: eigenvalues of the trailing 2 NB x 2 NB block of the active window ----
-        const int ns = 2 * LQ_NB;
+        // ---- chains and shifts: C chains of NB bulges; 2 NB C shifts = eigenvalues of the trailing block ----
+        int C = nw / 768;
+        C = std::max(1, std::min(C, LQ_MAXC));
+        const int ns = 2 * LQ_NB * C;
+        const int npairs = LQ_NB * C;
+        hshift.resize(2 * ns);
+        hpairs.resize(4 * npairs);
         lq_copy(s, H + (size_t)(iend - ns) + (size_t)(iend - ns) * n, n, dBlk, ns, ns, ns);
         if (since_deflation % 6 == 0) {
             // exceptional shifts (in the spirit of src/GenericSchur.jl:614-627): perturb the trailing diagonal
@@ -432,7 +546,7 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
                 else re.push_back(z);
             }
             int np = 0;
-            for (size_t j = 0; j + 1 < cp.size() && np < LQ_NB; j += 2, ++np) {
+            for (size_t j = 0; j + 1 < cp.size() && np < npairs; j += 2, ++np) {
                 std::complex<double> a = cp[j];
                 hpairs[4 * np] = a.real();
                 hpairs[4 * np + 1] = fabs(a.imag());
@@ -440,69 +554,107 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
                 hpairs[4 * np + 3] = -fabs(a.imag());
             }
             std::sort(re.begin(), re.end(), [](const std::complex<double>& x, const std::complex<double>& y) { return x.real() < y.real(); });
-            for (size_t j = 0; j < re.size() && np < LQ_NB; j += 2, ++np) {
+            for (size_t j = 0; j < re.size() && np < npairs; j += 2, ++np) {
                 const double a = re[j].real(), b2 = (j + 1 < re.size()) ? re[j + 1].real() : re[j].real();
                 hpairs[4 * np] = a;
                 hpairs[4 * np + 1] = 0.0;
                 hpairs[4 * np + 2] = b2;
                 hpairs[4 * np + 3] = 0.0;
             }
-            for (; np < LQ_NB; ++np) {   // not enough shifts (cannot happen with ns = 2 NB): repeat the last pair
+            for (; np < npairs; ++np)
                 for (int q = 0; q < 4; ++q) hpairs[4 * np + q] = hpairs[4 * (np - 1) + q];
-            }
         }
-        LG_TRY(cudaMemcpyAsync(dShift, hpairs.data(), sizeof(double) * 4 * LQ_NB, cudaMemcpyHostToDevice, s));
+        LG_TRY(cudaMemcpyAsync(dShift, hpairs.data(), sizeof(double) * 4 * npairs, cudaMemcpyHostToDevice, s));
         t_shift += now() - t0;
         t0 = now();
-        // ---- chase the chain from the top (L = istart) to the bottom (I = iend) ----
+        // ---- chase the chains from the top (L = istart) to the bottom (I = iend) ----
         const int L = istart, I = iend;
-        const int tau_end = (I - 1 - L) + 4 * (LQ_NB - 1);        // last time step with an active bulge
+        const int tau_end = (I - 1 - L) + 4 * (LQ_NB - 1) + (C - 1) * LQ_DELTA;   // last time step with an active bulge
+        const int Mfull = LQ_W - (4 * (LQ_NB - 1) + 6);
         wins.clear();
-        for (int tau0 = 0; tau0 <= tau_end;) {
-            // window for M steps: from the trailing active bulge's column - 1 to the leading active bulge's end + 3
-            int M = LQ_W - (4 * (LQ_NB - 1) + 6);
-            if (tau0 + M - 1 > tau_end) M = tau_end - tau0 + 1;
-            int pmin = 1 << 30, pmax = -1;
-            for (int b = 0; b < LQ_NB; ++b) {
-                const int p0 = L + tau0 - 4 * b, p1 = L + tau0 + M - 1 - 4 * b;
-                if (p1 < L || p0 > I - 1) continue;
-                pmin = std::min(pmin, std::max(p0, L));
-                pmax = std::max(pmax, std::min(p1, I - 1));
+        for (int tau0 = 0; tau0 <= tau_end; tau0 += Mfull) {
+            Win wn{};
+            wn.tau0 = tau0;
+            wn.M = std::min(Mfull, tau_end - tau0 + 1);
+            bool any = false;
+            for (int c = 0; c < LQ_MAXC; ++c) {
+                wn.wlo[c] = 1;
+                wn.whi[c] = 0;
+                if (c >= C) continue;
+                int pmin = 1 << 30, pmax = -1;
+                for (int b = 0; b < LQ_NB; ++b) {
+                    const int p0 = L + tau0 - 4 * b - c * LQ_DELTA, p1 = p0 + wn.M - 1;
+                    if (p1 < L || p0 > I - 1) continue;
+                    pmin = std::min(pmin, std::max(p0, L));
+                    pmax = std::max(pmax, std::min(p1, I - 1));
+                }
+                if (pmax < 0) continue;
+                wn.wlo[c] = std::max(L, pmin - 1);
+                wn.whi[c] = std::min(I, pmax + 3);
+                if (wn.whi[c] - wn.wlo[c] + 1 > LQ_W) { *err = "internal: chase window too large"; cudaFreeAsync(base, s); return -2; }
+                any = true;
             }
-            if (pmax >= 0) {
-                Win wn{tau0, M, std::max(L, pmin - 1), std::min(I, pmax + 3)};
-                if (wn.whi - wn.wlo + 1 > LQ_W) { *err = "internal: chase window too large"; cudaFreeAsync(base, s); return -2; }
-                wins.push_back(wn);
-            }
-            tau0 += M;
+            if (any) wins.push_back(wn);
         }
         const int nwin = (int)wins.size();
         for (int t = 0; t < nwin; ++t) {
             const Win& wn = wins[t];
-            double* U = (t & 1) ? dU1 : dU;
-            // stream A: chase, then the near columns the next window is going to need
+            LqChaseArgs ca{};
+            LqApplyArgs near{}, farl{}, topz{};
+            near.C = farl.C = topz.C = C;
+            near.mode = 1;
+            farl.mode = 1;
+            topz.mode = 2 | 4;
+            int gnear = 0, gfarl = 0, gtopz = 0;
+            for (int c = 0; c < LQ_MAXC; ++c) {
+                double* U = dUall + ((size_t)(t & 1) * LQ_MAXC + c) * LQ_W * LQ_W;
+                ca.wlo[c] = wn.wlo[c];
+                ca.whi[c] = wn.whi[c];
+                ca.U[c] = U;
+                const int wsz = wn.whi[c] - wn.wlo[c] + 1;
+                near.wlo[c] = farl.wlo[c] = topz.wlo[c] = wn.wlo[c];
+                near.wsz[c] = farl.wsz[c] = topz.wsz[c] = (c < C) ? wsz : 0;
+                near.U[c] = farl.U[c] = topz.U[c] = U;
+                if (c >= C || wsz <= 0) continue;
+                int nearhi = wn.whi[c];
+                if (t + 1 < nwin && wins[t + 1].whi[c] >= wins[t + 1].wlo[c]) nearhi = std::min(n, std::max(nearhi, wins[t + 1].whi[c]));
+                near.lc0[c] = wn.whi[c] + 1;
+                near.lc1[c] = nearhi;
+                farl.lc0[c] = nearhi + 1;
+                farl.lc1[c] = n;
+                gnear += lq_strips(near.lc1[c] - near.lc0[c] + 1);
+                gfarl += lq_strips(farl.lc1[c] - farl.lc0[c] + 1);
+                gtopz += lq_strips(wn.wlo[c] - 1) + (Z ? lq_strips(n) : 0);
+            }
+            // stream A: chase all chains (one CTA each), then the near columns the next windows are going to need
             if (!(skip & 2)) {
-                lq_chase_kernel<<<1, 32 * (LQ_NB + LQ_UW), chase_smem, s>>>(H, n, L, I, dShift, wn.tau0, wn.M, wn.wlo, wn.whi, U);
+                lq_chase_kernel<<<C, 32 * (LQ_NB + LQ_UW), chase_smem, s>>>(H, n, L, I, dShift, wn.tau0, wn.M, ca);
                 note_launch();
             }
             LG_TRY(cudaEventRecord(evChase[t & 1], s));
-            const int nearhi = (t + 1 < nwin) ? std::min(n, std::max(wn.whi, wins[t + 1].whi)) : wn.whi;
             if (t >= 1) LG_TRY(cudaStreamWaitEvent(s, evFar[(t - 1) & 1], 0));
-            int rc = left_part(s, U, LQ_W, wn.wlo, wn.whi, wn.whi + 1, nearhi, dTmpA);
-            if (rc) { cudaFreeAsync(base, s); return rc; }
-            // stream B: everything else outside the window
+            if (gnear > 0) {
+                lq_apply_kernel<<<gnear, 256, apply_smem, s>>>(H, Z, n, near);
+                note_launch();
+            }
+            // stream B: everything else outside the windows (left strips first, then the right strips: they overlap)
             LG_TRY(cudaStreamWaitEvent(sB, evChase[t & 1], 0));
             if (!(skip & 1)) {
-                rc = left_part(sB, U, LQ_W, wn.wlo, wn.whi, nearhi + 1, n, dTmp);
-                if (rc == 0) rc = top_part(sB, U, LQ_W, wn.wlo, wn.whi, dTmp);
-                if (rc == 0) rc = z_part(sB, U, LQ_W, wn.wlo, wn.whi, dTmp);
+                if (gfarl > 0) {
+                    lq_apply_kernel<<<gfarl, 256, apply_smem, sB>>>(H, Z, n, farl);
+                    note_launch();
+                }
+                if (gtopz > 0) {
+                    lq_apply_kernel<<<gtopz, 256, apply_smem, sB>>>(H, Z, n, topz);
+                    note_launch();
+                }
             }
-            if (rc) { cudaFreeAsync(base, s); return rc; }
             LG_TRY(cudaEventRecord(evFar[t & 1], sB));
             if (stats) stats->windows += 1;
         }
         if (nwin > 0) LG_TRY(cudaStreamWaitEvent(s, evFar[(nwin - 1) & 1], 0));
         if (nwin > 1) LG_TRY(cudaStreamWaitEvent(s, evFar[(nwin - 2) & 1], 0));
+        LG_TRY(cudaGetLastError());
         t_enq += now() - t0;
         if (stats) stats->sweeps += 1;
     }
