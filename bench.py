@@ -324,6 +324,9 @@ def main():
         gs.gschur_device_(kind, n, batch, A.data_ptr(), Z.data_ptr(), w.data_ptr(), info.data_ptr(),
                           stats.data_ptr(), scale=True, stream=stream)
 
+    import ctypes
+    from genericschur_jl_b200 import _lib as _gl
+    _L = _gl.lib()
     for _ in range(args.warmup):
         A.copy_(A0)
         step()
@@ -348,6 +351,13 @@ def main():
     launches = gs.launch_count() - launches0
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
+    # per-kernel device times of one more (untimed) step: stage A = gehrd_q_kernel, stage B = gschur_qr_kernel
+    _L.gschur_cuda_stage_timing(1, None, None)
+    A.copy_(A0)
+    step()
+    ms_a, ms_b = ctypes.c_float(0), ctypes.c_float(0)
+    have_stage = _L.gschur_cuda_stage_timing(0, ctypes.byref(ms_a), ctypes.byref(ms_b)) == 0
+    torch.cuda.synchronize()
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -394,18 +404,36 @@ def main():
     if rank == 0:
         hbm_peak, hbm_src = measured_peaks()
         fp64_peak, _ = gs.measure_fp64_peak()
-        kernel_ms = float(np.mean(step_ms))            # one launch per step: the step IS the dominant kernel
-        alg_flops = flops_per_matrix * batch
+        # Dominant kernel: stage B (gschur_qr_kernel, QR iteration + Z).  Its algorithmic work is the nominal QR share
+        # of SURVEY.md §8d: 69.4 n^3 flops (complex) / 20.3 n^3 (real) per matrix; stage A has the remaining
+        # 18.67 n^3 / 4.67 n^3 (Hessenberg + Q).  Times: CUDA events recorded by the library on the launching stream.
+        step_mean = float(np.mean(step_ms))
+        qr_flops = (69.4 if kind == 1 else 20.3) * n ** 3
+        hq_flops = flops_per_matrix - qr_flops
+        kernel_ms = float(ms_b.value) if have_stage else step_mean
+        alg_flops = (qr_flops if have_stage else flops_per_matrix) * batch
         alg_bytes = 3 * n * n * esz * batch + n * 16 * batch
         achieved_tf = alg_flops / (kernel_ms * 1e-3) / 1e12
+        # DRAM traffic of the same kernel from the committed ncu capture (profiles/r01_stageB_cfg3.summary.txt):
+        # 643 MB for a 2960-matrix launch = 217 KB per 64x64 c64 matrix (H, Q in; T, Z out), scaled to this launch
+        ncu_traffic_per_matrix = 217.3e3 if (kind == 1 and n == 64) else None
         roofline = {
-            "bound": "fp64_fma", "kernel": "gschur_batched_kernel", "achieved": achieved_tf, "peak": fp64_peak,
-            "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": None,
+            "bound": "fp64_fma", "kernel": "gschur_qr_kernel<cx<double>,2> (stage B: QR sweeps + Z)" if kind == 1 else "gschur_qr_kernel (stage B)",
+            "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
+            "traffic": (ncu_traffic_per_matrix * batch) if ncu_traffic_per_matrix else None,
+            "traffic_note": "dram__bytes_read+write of one ncu --set full capture (2960-matrix launch), scaled per matrix",
+            "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / step_mean,
             "peak_source": "measured live (library DFMA micro-kernel; MEASURED_PEAKS.json has no FP64 figure)",
-            "algorithmic_flops_per_matrix": flops_per_matrix,
+            "algorithmic_flops_per_matrix": qr_flops if have_stage else flops_per_matrix,
             "executed_reflector_applications_per_matrix": executed_units,
-            "hbm_view": {"achieved": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+            "whole_step": {"achieved": flops_per_matrix * batch / (step_mean * 1e-3) / 1e12,
+                           "frac": flops_per_matrix * batch / (step_mean * 1e-3) / 1e12 / fp64_peak,
+                           "algorithmic_flops_per_matrix": flops_per_matrix},
+            "stage_a": {"kernel": "gehrd_q_kernel (scale + Hessenberg + Q)", "kernel_ms": float(ms_a.value) if have_stage else None,
+                        "achieved": (hq_flops * batch / (ms_a.value * 1e-3) / 1e12) if have_stage and ms_a.value > 0 else None,
+                        "algorithmic_flops_per_matrix": hq_flops},
+            "hbm_view": {"achieved": alg_bytes / (step_mean * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": alg_bytes / (step_mean * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                          "algorithmic_bytes_per_matrix": alg_bytes // batch},
         }
         cpu = None

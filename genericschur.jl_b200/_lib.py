@@ -27,6 +27,7 @@ EXPORTS = [
     "gschur_cuda_batched_async",
     "gschur_cuda_hessenberg_batched",
     "gschur_cuda_measure_fp64_peak",
+    "gschur_cuda_stage_timing",
     "gschur_cuda_hessenberg_large",
     "gschur_cuda_large",
     "gschur_cuda_dgemm",
@@ -69,6 +70,8 @@ def lib():
         cd = ctypes.c_double
         L.gschur_cuda_hessenberg_large.argtypes = [ci, vp, ci, vp, vp, ci, u32]
         L.gschur_cuda_hessenberg_large.restype = ci
+        L.gschur_cuda_stage_timing.argtypes = [ci, vp, vp]
+        L.gschur_cuda_stage_timing.restype = ci
         L.gschur_cuda_large.argtypes = [ci, vp, ci, vp, ci, vp, ci, vp, vp, u32]
         L.gschur_cuda_large.restype = ci
         L.gschur_cuda_dgemm.argtypes = [ci, ci, ci, ci, ci, cd, vp, ci, vp, ci, cd, vp, ci]

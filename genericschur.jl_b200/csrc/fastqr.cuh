@@ -1138,6 +1138,7 @@ template <class T, int CPL> int launch_fast(const BatchedParams& p_in, int dev_s
         counter2 = reinterpret_cast<unsigned long long*>(scratch + (size_t)p.batch * 8);
         e = cudaMemsetAsync(counter2, 0, sizeof(unsigned long long), stream);
         p.scratch = scratch;
+        stage_timing_mark(0, stream);
         int rc = launch_gehrd<T, 64>(p, dev_sms, stream, err);
         if (rc) {
             cudaFreeAsync(scratch, stream);
@@ -1145,6 +1146,7 @@ template <class T, int CPL> int launch_fast(const BatchedParams& p_in, int dev_s
         }
         p.counter = counter2;   // stage B gets its own work-queue head
     }
+    stage_timing_mark(1, stream);
     auto kern = gschur_qr_kernel<T, CPL>;
     size_t smem = fast_smem_layout<T, CPL>::bytes(p.n);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1164,6 +1166,7 @@ template <class T, int CPL> int launch_fast(const BatchedParams& p_in, int dev_s
         if (grid > p.batch) grid = p.batch;
         kern<<<(unsigned)grid, 64, smem, stream>>>(p);
         note_launch();
+        stage_timing_mark(2, stream);
         e = cudaGetLastError();
         if (e != cudaSuccess) {
             *err = std::string("qr kernel launch: ") + cudaGetErrorString(e);

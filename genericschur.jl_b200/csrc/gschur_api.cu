@@ -403,6 +403,13 @@ const char* gschur_cuda_last_error(void) { return g_err.c_str(); }
 
 uint64_t gschur_cuda_launch_count(void) { return gs::launch_counter(); }
 
+// per-stage device times (ms) of the most recent two-kernel batched call while timing is enabled
+int gschur_cuda_stage_timing(int enable, float* ms_stage_a, float* ms_stage_b) {
+    if (enable >= 0) gs::stage_timing_enable(enable != 0);
+    if (ms_stage_a && ms_stage_b) return gs::stage_timing_read(ms_stage_a, ms_stage_b);
+    return 0;
+}
+
 int gschur_cuda_max_batched_n(int kind) {
     if (kind < 0 || kind > 3) return 0;
     return max_schur_n(kind);

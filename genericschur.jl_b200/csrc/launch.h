@@ -28,6 +28,12 @@ enum { F_HESS_INPUT = 0x2u, F_CHECK_SUBDIAG = 0x4u };
 void note_launch();
 unsigned long long launch_counter();
 
+// optional per-stage timing of the two-kernel path (bench.py's per-kernel roofline): CUDA events on the launching stream
+void stage_timing_enable(bool on);
+bool stage_timing_enabled();
+void stage_timing_mark(int which, cudaStream_t s);      // which = 0: before stage A, 1: between, 2: after stage B
+int stage_timing_read(float* ms_a, float* ms_b);        // synchronises on the last events; 0 = ok
+
 // dynamic shared memory one CTA needs for an n x n matrix of `kind`
 size_t batched_smem_bytes(int kind, int n);
 

@@ -101,6 +101,13 @@ int gschur_cuda_batched_async(int kind, int n, int64_t batch,
 int gschur_cuda_measure_fp64_peak(double* tflops, double* ms);
 
 /*
+ * Per-kernel timing of the two-kernel batched path (stage A: scale + Hessenberg + Q; stage B: QR iteration), used by
+ * bench.py for the per-kernel roofline.  enable: 1 / 0 switches CUDA-event recording on the launching stream on / off,
+ * -1 leaves it unchanged; when both pointers are given the times (ms) of the most recent call are returned.
+ */
+int gschur_cuda_stage_timing(int enable, float* ms_stage_a, float* ms_stage_b);
+
+/*
  * Batched Householder reduction to Hessenberg form, A_b = Q_b H_b Q_b^H.
  * Replaces _hessenberg!(A) src/hessenberg.jl:3-17 (LinearAlgebra.hessenberg! src/pirates.jl:232) and
  * _materializeQ(H) src/hessenberg.jl:150-166.
