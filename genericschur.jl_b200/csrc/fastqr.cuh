@@ -211,9 +211,13 @@ template <class T, int CPL> struct FastSolver {
     }
     GS_DEV ZOp* slot() { return ring + (sidx & 1) * cap + cnt; }
     // make room for m ops once, so that the step loop can push without checking
-    GS_DEV void reserve_ops(int m) { ensure_space(m < cap ? m : cap); }
+    GS_DEV void reserve_ops(int) {}   // (the ring is small: every push checks for space, see push_*)
     GS_DEV void push_refl_c(int k, const C& tau1, const C& v2) {
         if (!wantZ) return;
+        if (cnt == cap) {
+            publish(0);
+            begin_buffer();
+        }
         if (lane == 0) {
             ZOp* e = ring + (sidx & 1) * cap + cnt;
             if constexpr (CPLX) {
@@ -229,6 +233,10 @@ template <class T, int CPL> struct FastSolver {
     }
     GS_DEV void push_r(int op, int k, const R& a0, const R& a1, const R& a2) {
         if (!wantZ) return;
+        if (cnt == cap) {
+            publish(0);
+            begin_buffer();
+        }
         if (lane == 0) {
             ZOp* e = ring + (sidx & 1) * cap + cnt;
             if constexpr (!CPLX) {
@@ -982,9 +990,14 @@ template <class T, int CPL> struct fast_smem_layout {
     typedef smem_layout<T> L;
     typedef FastSolver<T, CPL> FS;
     typedef zop_t<etraits<T>::is_complex, typename etraits<T>::real> ZOp;
-    __host__ __device__ static int cap(int n) { return n + 8; }
+    // A short ring (16 reflectors per buffer, two buffers): the H-warp publishes every 16 bulge steps.  Together with
+    // dropping the eigenvalue array for complex kinds (their eigenvalues are diag(T)) this brings a 64x64 ComplexF64
+    // matrix to 36.9 KB of shared memory: six CTAs per SM instead of five.
+    __host__ __device__ static int cap(int) { return 16; }
     __host__ __device__ static size_t off_w(int n) { return L::up16((size_t)FS::packed_elems(n) * sizeof(T)); }
-    __host__ __device__ static size_t off_ring(int n) { return off_w(n) + L::up16((size_t)n * 2 * sizeof(R)); }
+    __host__ __device__ static size_t off_ring(int n) {
+        return off_w(n) + (etraits<T>::is_complex ? 0 : L::up16((size_t)n * 2 * sizeof(R)));
+    }
     __host__ __device__ static size_t off_hdr(int n) { return off_ring(n) + L::up16(2 * (size_t)cap(n) * sizeof(ZOp)); }
     __host__ __device__ static size_t bytes(int n) { return off_hdr(n) + L::up16(sizeof(zring_hdr)); }
 };

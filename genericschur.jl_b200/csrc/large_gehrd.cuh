@@ -16,7 +16,8 @@ namespace gs {
 
 constexpr int LG_NB = 32;          // panel width
 constexpr int LG_PT = 512;         // threads of the single-CTA panel kernel (128 registers each: 32 running sums)
-constexpr int LG_GEMV_ROWS = 128;  // rows per gemv CTA (one row per thread)
+constexpr int LG_GEMV_ROWS = 512;  // rows per gemv CTA (two rows per thread, 128-bit loads: 4 KB contiguous per column and CTA)
+constexpr int LG_MAXCHUNKS = 64;   // column chunks of the panel gemv (partial sums are reduced by the next panel kernel)
 
 struct LargeWork {
     int n, nb;
@@ -65,8 +66,8 @@ __global__ void __launch_bounds__(LG_PT) lg_panel_col_kernel(LargeWork w, int p,
         const int j = nbv - 1;                        // 0-based index of the previous reflector
         const double tauj = w.tsave[w.nb];
         for (int rr = tid; rr < m; rr += LG_PT) {
-            double y = 0.0;
-            for (int ch = 0; ch < w.chunks; ++ch) y += w.ypart[(size_t)ch * n + r0 + rr];
+            double y = w.ypart[r0 + rr];          // accumulated by the gemv CTAs with atomicAdd
+            w.ypart[r0 + rr] = 0.0;               // ready for the next gemv
             for (int q = 0; q < j; ++q) y -= Yp[rr + (size_t)q * n] * w.tsave[q];
             Yp[rr + (size_t)j * n] = tauj * y;
         }
@@ -216,8 +217,8 @@ __global__ void __launch_bounds__(LG_PT) lg_panel_finish_kernel(LargeWork w, int
     const int j = ib - 1;
     const double tauj = w.tsave[w.nb];
     for (int rr = tid; rr < m; rr += LG_PT) {
-        double y = 0.0;
-        for (int ch = 0; ch < w.chunks; ++ch) y += w.ypart[(size_t)ch * n + r0 + rr];
+        double y = w.ypart[r0 + rr];
+        w.ypart[r0 + rr] = 0.0;
         for (int q = 0; q < j; ++q) y -= Yp[rr + (size_t)q * n] * w.tsave[q];
         Yp[rr + (size_t)j * n] = tauj * y;
     }
@@ -231,37 +232,58 @@ __global__ void __launch_bounds__(LG_PT) lg_panel_finish_kernel(LargeWork w, int
     }
 }
 
-// The memory-bound kernel: ypart[chunk][r] = sum_{col in chunk} A(r, col) * v[col] for rows r0..n-1, columns c0..n-1.
-// One row per thread (coalesced along the column-major rows), LG_GEMV_ROWS rows per CTA, `chunks` column chunks.
-__global__ void __launch_bounds__(LG_GEMV_ROWS) lg_gemv_kernel(LargeWork w, int r0, int c0) {
+// The memory-bound kernel: y[r] += sum_{col in chunk} A(r, col) * v[col] for rows r0..n-1, columns c0..n-1.
+// One row per thread (coalesced along the column-major rows), LG_GEMV_ROWS rows per CTA, `chunks` column chunks whose
+// partial sums are combined with FP64 atomicAdd in L2 (y is cleared by the panel kernel that consumes it).
+__global__ void __launch_bounds__(LG_GEMV_ROWS / 2) lg_gemv_kernel(LargeWork w, int r0, int c0) {
+    // two consecutive rows per thread through one 128-bit load (rows start at an even index; n is even for that path)
     const int n = w.n;
-    const int r = r0 + blockIdx.x * LG_GEMV_ROWS + threadIdx.x;
+    const bool vec2 = (n % 2 == 0);
+    const int rbase = vec2 ? (r0 & ~1) : r0;
+    const int r = rbase + blockIdx.x * LG_GEMV_ROWS + 2 * threadIdx.x;
     const int ncols = n - c0;
     const int per = (ncols + w.chunks - 1) / w.chunks;
     const int cb = c0 + blockIdx.y * per;
     const int ce = min(cb + per, n);
     __shared__ double vs[512];
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;      // a*: row r, b*: row r+1 (two accumulators each)
     for (int cc = cb; cc < ce; cc += 512) {
         const int cnt = min(512, ce - cc);
         __syncthreads();
-        for (int t = threadIdx.x; t < cnt; t += LG_GEMV_ROWS) vs[t] = w.vcur[cc + t];
+        for (int t = threadIdx.x; t < cnt; t += LG_GEMV_ROWS / 2) vs[t] = w.vcur[cc + t];
         __syncthreads();
-        if (r < n) {
-            const double* ap = w.A + (size_t)r + (size_t)cc * n;
+        if (r + 1 < n && vec2) {
+            const double2* ap = reinterpret_cast<const double2*>(w.A + (size_t)r + (size_t)cc * n);
+            const size_t st = (size_t)n / 2;
             int t = 0;
-            for (; t + 4 <= cnt; t += 4) {
-                const double a0 = __ldg(ap + (size_t)(t + 0) * n), a1 = __ldg(ap + (size_t)(t + 1) * n);
-                const double a2 = __ldg(ap + (size_t)(t + 2) * n), a3 = __ldg(ap + (size_t)(t + 3) * n);
-                acc0 = fma(a0, vs[t + 0], acc0);
-                acc1 = fma(a1, vs[t + 1], acc1);
-                acc2 = fma(a2, vs[t + 2], acc2);
-                acc3 = fma(a3, vs[t + 3], acc3);
+            for (; t + 8 <= cnt; t += 8) {       // 8 independent 128-bit loads in flight per thread
+                double2 x[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) x[u] = __ldg(ap + (size_t)(t + u) * st);
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    a0 = fma(x[u].x, vs[t + u], a0);
+                    b0 = fma(x[u].y, vs[t + u], b0);
+                    a1 = fma(x[u + 1].x, vs[t + u + 1], a1);
+                    b1 = fma(x[u + 1].y, vs[t + u + 1], b1);
+                }
             }
-            for (; t < cnt; ++t) acc0 = fma(__ldg(ap + (size_t)t * n), vs[t], acc0);
+            for (; t < cnt; ++t) {
+                const double2 x = __ldg(ap + (size_t)t * st);
+                a0 = fma(x.x, vs[t], a0);
+                b0 = fma(x.y, vs[t], b0);
+            }
+        } else if (r < n) {
+            for (int t = 0; t < cnt; ++t) {
+                a0 = fma(w.A[(size_t)r + (size_t)(cc + t) * n], vs[t], a0);
+                if (r + 1 < n) b0 = fma(w.A[(size_t)r + 1 + (size_t)(cc + t) * n], vs[t], b0);
+            }
         }
     }
-    if (r < n) w.ypart[(size_t)blockIdx.y * n + r] = (acc0 + acc1) + (acc2 + acc3);
+    if (cb < ce) {
+        if (r >= r0 && r < n) atomicAdd(&w.ypart[r], a0 + a1);
+        if (r + 1 >= r0 && r + 1 < n) atomicAdd(&w.ypart[r + 1], b0 + b1);
+    }
 }
 
 __global__ void lg_set_identity_kernel(double* Q, int n) {
@@ -309,8 +331,13 @@ inline int lg_gehrd(LargeWork& w, double* Q, cudaStream_t s, std::string* err) {
             lg_panel_col_kernel<<<1, LG_PT, smem_panel, s>>>(w, p, i);
             note_launch();
             // y = A(r0.., p+i ..) * v    (v has its leading 1 at row p+i)
-            dim3 grid((m + LG_GEMV_ROWS - 1) / LG_GEMV_ROWS, w.chunks);
-            lg_gemv_kernel<<<grid, LG_GEMV_ROWS, 0, s>>>(w, r0, p + i);
+            const int rowblocks = (m + 1 + LG_GEMV_ROWS - 1) / LG_GEMV_ROWS;
+            int ch = (1184 + rowblocks - 1) / rowblocks;          // ~8 CTAs per SM
+            ch = ch < 8 ? 8 : (ch > LG_MAXCHUNKS ? LG_MAXCHUNKS : ch);
+            if (ch > (n - (p + i) + 63) / 64) ch = (n - (p + i) + 63) / 64 > 0 ? (n - (p + i) + 63) / 64 : 1;
+            w.chunks = ch;
+            dim3 grid(rowblocks, ch);
+            lg_gemv_kernel<<<grid, LG_GEMV_ROWS / 2, 0, s>>>(w, r0, p + i);
             note_launch();
         }
         lg_panel_finish_kernel<<<1, LG_PT, 0, s>>>(w, p, ib);
@@ -355,7 +382,7 @@ inline int lg_gehrd(LargeWork& w, double* Q, cudaStream_t s, std::string* err) {
 inline int lg_alloc(LargeWork& w, int n, cudaStream_t s, std::string* err) {
     w.n = n;
     w.nb = LG_NB;
-    w.chunks = 16;
+    w.chunks = LG_MAXCHUNKS;
     const size_t nn = (size_t)n * n;
     const int npanels = (n + w.nb - 1) / w.nb + 1;
     double* base = nullptr;
@@ -370,6 +397,7 @@ inline int lg_alloc(LargeWork& w, int n, cudaStream_t s, std::string* err) {
     w.vcur = w.ypart + (size_t)w.chunks * n;
     w.tau = w.vcur + n;
     w.tsave = w.tau + n;
+    LG_TRY(cudaMemsetAsync(w.ypart, 0, (size_t)n * sizeof(double), s));
     return 0;
 }
 inline void lg_free(LargeWork& w, cudaStream_t s) {
