@@ -24,7 +24,12 @@
 // The arithmetic per reflector application and every decision rule are those of batched.cuh (and of the
 // reference, src/GenericSchur.jl:194-335, 374-504, 513-699, 837-952); only the schedule and the layout differ.
 #pragma once
+#include <cstdlib>
 #include "gehrd.cuh"
+
+#ifndef GS_ZRUN
+#define GS_ZRUN 8
+#endif
 
 namespace gs {
 
@@ -105,6 +110,23 @@ template <> GS_DEV void sts_e<cx<double>>(uint32_t a, const cx<double>& v) {
     asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(a), "d"(v.re), "d"(v.im) : "memory");
 }
 
+// predicated shared-memory accesses (guaranteed branch-free inside the step loops)
+GS_DEV void sts_c64_if(uint32_t a, const cx<double>& v, bool p) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %3, 0; @q st.shared.v2.f64 [%0], {%1, %2}; }" ::"r"(a), "d"(v.re), "d"(v.im),
+                 "r"((int)p)
+                 : "memory");
+}
+GS_DEV void lds_c64_if(cx<double>& v, uint32_t a, bool p) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %3, 0; @q ld.shared.v2.f64 {%0, %1}, [%2]; }"
+                 : "+d"(v.re), "+d"(v.im)
+                 : "r"(a), "r"((int)p));
+}
+GS_DEV void sts_2i_if(uint32_t a, int x, int y, bool p) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %3, 0; @q st.shared.v2.b32 [%0], {%1, %2}; }" ::"r"(a), "r"(x), "r"(y),
+                 "r"((int)p)
+                 : "memory");
+}
+
 template <class T, int CPL> struct FastSolver {
     typedef typename etraits<T>::real R;
     typedef cx<R> C;
@@ -122,6 +144,9 @@ template <class T, int CPL> struct FastSolver {
     unsigned* stp;
     // producer state (uniform across the H-warp)
     int sidx, cnt;
+#ifdef GS_QR_PROFILE
+    long long prof[4];
+#endif
 
     __host__ __device__ static int colbase(int j) { return ((j - 1) * (j + 2 * EX)) / 2; }   // offset of column j
     __host__ __device__ static int packed_elems(int n) { return (n * (n + 1)) / 2 + EX * n; }
@@ -144,8 +169,8 @@ template <class T, int CPL> struct FastSolver {
             R ab = r_max(a1, a2), ba = r_min(a1, a2);
             R d1 = abs1(hc1), d2 = abs1(hcc - hc1);
             R aa = r_max(d1, d2), bb = r_min(d1, d2);
-            R s = aa + ab;
-            if (ba * (ab / s) <= r_max(smallnum, ulp * (bb * (aa / s)))) return true;
+            R rs = q_rcp(aa + ab);
+            if (ba * (ab * rs) <= r_max(smallnum, ulp * (bb * (aa * rs)))) return true;
         }
         return false;
     }
@@ -188,7 +213,13 @@ template <class T, int CPL> struct FastSolver {
     // ------------------------------------------------------------------------------------------------
     GS_DEV void begin_buffer() {
         if (!wantZ) return;
+#ifdef GS_QR_PROFILE
+        const long long tb0 = clock64();
+#endif
         if (sidx >= 2) named_bar_sync(BAR_EMPTY0 + (sidx & 1), 64);
+#ifdef GS_QR_PROFILE
+        prof[1] += clock64() - tb0;
+#endif
         cnt = 0;
     }
     GS_DEV void publish(int end) {
@@ -450,8 +481,328 @@ template <class T, int CPL> struct FastSolver {
         __syncwarp();
     }
 
+    // ================================================================================================
+    // complex single shift, software-pipelined (ComplexF64).
+    //
+    // The 2x2 diagonal block the bulge sits on (and the sub-diagonal entry below it) lives in registers, replicated
+    // in every lane, so the chain  reflector k -> block update -> reflector k+1  never touches shared memory and
+    // needs no lane hand-off.  Every other entry of rows k, k+1 (columns >= k+2: "left items") and of columns
+    // k, k+1 (rows <= k-1: "right items") is a bulk item: lane l owns the indices l+1+32s and holds one running
+    // entry per index (H[k, j] of its column while j >= k+2, H[j, k] of its row once j <= k-1).  One loop iteration
+    // applies reflector k to the bulk items AND forms reflector k+1 from the register block; the two instruction
+    // streams are independent and sit in one basic block, so the long sqrt / reciprocal chain of the reflector is
+    // overlapped with the bulk arithmetic.  One __syncwarp per step orders the shared-memory traffic.
+    // Same arithmetic per entry as src/GenericSchur.jl:426-459 (left: :442-446, right: :448-452).
+    // ================================================================================================
+    GS_DEV void late_start_step(int k0, int iend, C v0, C v1) {
+        // the first step of a sweep that starts inside the active block (src/GenericSchur.jl:461-482), in shared memory
+        const R zero = r_const<R>(0.0), one = r_const<R>(1.0);
+        const C tau1 = reflector_cplx2(v0, v1);
+        const C v2 = v1, v2c = cconj(v1), tau1c = cconj(tau1);
+        const R tau2 = (tau1 * v2).re;
+        push_refl_c(k0, tau1, v2);
+        for (int j = k0 + lane; j <= n; j += 32) {
+            const C a = HH(k0, j), b = HH(k0 + 1, j);
+            const C ss = tau1c * a + tau2 * b;
+            HH(k0, j) = a - ss;
+            HH(k0 + 1, j) = b - ss * v2;
+        }
+        __syncwarp();
+        const int jmax = (k0 + 2 < iend) ? k0 + 2 : iend;
+        for (int i = 1 + lane; i <= jmax; i += 32) {
+            const C d = HH(i, k0), e = HH(i, k0 + 1);
+            const C ss = tau1 * d + tau2 * e;
+            HH(i, k0) = d - ss;
+            HH(i, k0 + 1) = e - ss * v2c;
+        }
+        __syncwarp();
+        C t = mk_cx<R>(one, zero) - tau1;
+        R at = c_abs(t);
+        t = mk_cx<R>(t.re / at, t.im / at);
+        const C tc = cconj(t);
+        if (lane == 0) {
+            HH(k0 + 1, k0) = HH(k0 + 1, k0) * tc;
+            if (k0 + 2 <= iend) HH(k0 + 2, k0 + 1) = HH(k0 + 2, k0 + 1) * t;
+        }
+        __syncwarp();
+        for (int j = k0; j <= iend; ++j) {
+            if (j == k0 + 1) continue;
+            for (int c = j + 1 + lane; c <= n; c += 32) HH(j, c) = HH(j, c) * t;
+            for (int r = 1 + lane; r <= j - 1; r += 32) HH(r, j) = HH(r, j) * tc;
+            __syncwarp();
+        }
+        emit_scale_c(k0, k0, tc);
+        emit_scale_c(k0 + 2, iend, tc);
+    }
+
+    GS_DEV static double flip_if(double x, unsigned m) {   // x with its sign bit xor-ed by m (0 or 0x80000000)
+        return __hiloint2double(__double2hiint(x) ^ (int)m, __double2loint(x));
+    }
+
+    GS_DEV void sweep_complex_pipelined(const C& shift, int istart, int iend) {
+        static_assert(sizeof(R) == 8, "ComplexF64 only");
+#ifdef GS_QR_PROFILE
+        const long long tp0 = clock64();
+#endif
+        const R zero = 0.0;
+        const R ulp = rtraits<R>::eps();
+        int istart1 = 0;
+        for (int base = iend - 1; base >= istart + 1 && !istart1; base -= 32) {
+            int mm = base - lane;
+            bool hit = false;
+            if (mm >= istart + 1) {
+                const C h11 = HH(mm, mm), h22 = HH(mm + 1, mm + 1);
+                const C h11s = h11 - shift;
+                const R h21 = HH(mm + 1, mm).re;
+                const R rs = q_rcp(abs1(h11s) + r_abs(h21));
+                const R h10 = HH(mm, mm - 1).re;
+                hit = r_abs(h10) * r_abs(h21 * rs) <=
+                      ulp * ((r_abs(h11s.re * rs) + r_abs(h11s.im * rs)) * (abs1(h11) + abs1(h22)));
+            }
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) istart1 = base - (__ffs(m) - 1);
+        }
+        if (!istart1) istart1 = istart;
+        const int k0 = istart1;
+        C v0, v1;
+        {
+            C h11s = HH(k0, k0) - shift;
+            R h21 = HH(k0 + 1, k0).re;
+            R rs = q_rcp(abs1(h11s) + r_abs(h21));
+            v0 = mk_cx<R>(h11s.re * rs, h11s.im * rs);
+            v1 = mk_cx<R>(h21 * rs, zero);
+        }
+        int kf = k0;
+        bool store_sub = false;   // does step kf write (beta, 0) into column kf-1 ?
+        unsigned napplied = 0;
+        if (k0 > istart) {
+            late_start_step(k0, iend, v0, v1);
+            napplied = 1;
+            kf = k0 + 1;
+            store_sub = true;
+            if (kf <= iend - 1) {
+                v0 = HH(kf, kf - 1);
+                v1 = HH(kf + 1, kf - 1);
+            }
+        }
+#ifdef GS_QR_PROFILE
+        const long long tp1 = clock64();
+        (void)tp0;
+#endif
+        if (kf > iend - 1) {
+            // the late-start step was the only one: make the tail sub-diagonal real (src/GenericSchur.jl:486-500)
+            stp[1] += napplied;
+            C t = HH(iend, iend - 1);
+            if (t.im != zero) {
+                R rt = c_abs(t);
+                t = mk_cx<R>(t.re / rt, t.im / rt);
+                const C tc = cconj(t);
+                for (int cidx = iend + 1 + lane; cidx <= n; cidx += 32) HH(iend, cidx) = HH(iend, cidx) * tc;
+                for (int r = 1 + lane; r <= iend - 1; r += 32) HH(r, iend) = HH(r, iend) * t;
+                emit_scale_c(iend, iend, t);
+                __syncwarp();
+                if (lane == 0) HH(iend, iend - 1) = mk_cx<R>(rt, zero);
+            }
+            __syncwarp();
+            return;
+        }
+        constexpr uint32_t ES = (uint32_t)sizeof(T);
+        const uint32_t hb = smem_u32(H);
+        // Bulk items.  Index j = lane+1+32s is a LEFT item (column j, rows k, k+1) while j >= k+2 and a RIGHT item
+        // (row j, columns k, k+1) once j <= k-1.  Right items are held CONJUGATED: conj(ss) = conj(tau1) conj(x) +
+        // tau2 conj(y), conj(x') = conj(x) - conj(ss), conj(y') = conj(y) - conj(ss) v2 — the left item's formulas —
+        // so one instruction stream with fixed coefficients serves both roles; only the imaginary sign of what is
+        // loaded / stored differs (xor mask sg).  Entries enter and leave the register block through shared memory.
+        uint32_t ca[CPL], ib[CPL];
+        int jl[CPL];
+        C c[CPL];
+        uint32_t ak = hb + ES * (uint32_t)(colbase(kf) - 1);   // column k, "row 0"
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+            const int j = lane + 1 + 32 * s;
+            const bool valid = j <= n;
+            jl[s] = valid ? j : -(1 << 28);
+            ca[s] = hb + ES * (uint32_t)(colbase(valid ? j : 1) - 1);
+            ib[s] = ES * (uint32_t)(valid ? j : 1);
+            c[s] = mk_cx<R>(zero, zero);
+            if (jl[s] >= kf + 2) c[s] = lds_e<T>(ca[s] + ES * kf);
+            else if (j <= kf - 1) c[s] = cconj(lds_e<T>(ak + ib[s]));
+        }
+        // register block: d00 d01 / d10 d11 = H[k..k+1, k..k+1], e1 = H[k+2, k+1] (0 past the active block).  The first
+        // column is carried in registers, the second one is picked up from shared memory at the top of each step.
+        C d00 = HH(kf, kf), d10 = HH(kf + 1, kf);
+        C tau1 = reflector_cplx2(v0, v1);
+        R beta = v0.re;
+        C v2 = v1;
+        C f_sub, f_diag, f_sup;   // H[iend, iend-1], H[iend, iend], H[iend-1, iend] after the last step
+        const int capz = wantZ ? cap : 0x7fffffff;
+        const uint32_t ring32 = smem_u32(ring);
+#ifdef GS_QR_PROFILE
+        const long long tp2 = clock64();
+        prof[2] += tp2 - tp1;
+#endif
+        for (int k = kf;; ++k) {
+            if (cnt == capz) {
+                publish(0);
+                begin_buffer();
+            }
+            __syncwarp();
+            const uint32_t kb = ES * (uint32_t)k;
+            const uint32_t ak1 = ak + ES * (uint32_t)(k + EX);        // column k+1
+            // ---- loads: column k+1 of the block; second entry of every bulk item ----
+            const C d01 = lds_e<T>(ak1 + kb), d11 = lds_e<T>(ak1 + kb + ES);
+            C e1 = mk_cx<R>(zero, zero);
+            if (k + 2 <= iend) e1 = lds_e<T>(ak1 + kb + 2 * ES);
+            bool act[CPL], own2[CPL];
+            unsigned sg[CPL];
+            uint32_t sa[CPL];
+            C y[CPL];
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const int j = lane + 1 + 32 * s;
+                const bool isL = jl[s] >= k + 2;
+                const bool isR = j <= k - 1;
+                act[s] = isL || isR;
+                own2[s] = jl[s] == k + 2;
+                sg[s] = isR ? 0x80000000u : 0u;
+                sa[s] = isR ? ak + ib[s] : ca[s] + kb;                  // inactive lanes: a harmless address
+                const uint32_t ya = isR ? ak1 + ib[s] : sa[s] + ES;
+                C xr = mk_cx<R>(c[s].re, -c[s].im);
+                lds_c64_if(xr, sa[s], j == k - 1);                      // row k-1 left the register block: H[k-1, k]
+                c[s].re = xr.re;
+                c[s].im = -xr.im;
+                y[s] = lds_e<T>(ya);
+                y[s].im = flip_if(y[s].im, sg[s]);
+            }
+            const R tau2 = tau1.re * v2.re - tau1.im * v2.im;
+            const C tau1c = cconj(tau1), v2c = cconj(v2);
+            // ---- chain: rows k, k+1 of columns k, k+1 (left), then columns k, k+1 of rows k..k+2 (right) ----
+            const C ss0 = tau1c * d00 + tau2 * d10;
+            const C a00 = d00 - ss0, a10 = d10 - ss0 * v2;
+            const C ss1 = tau1c * d01 + tau2 * d11;
+            const C a01 = d01 - ss1, a11 = d11 - ss1 * v2;
+            const C sr1 = tau1 * a10 + tau2 * a11;
+            const C n_v0 = a10 - sr1, n_d00 = a11 - sr1 * v2c;      // H[k+1, k], H[k+1, k+1]
+            const C n_v1 = (-tau2) * e1, n_d10 = e1 + n_v1 * v2c;   // H[k+2, k] (the bulge), H[k+2, k+1]
+            const C sr0 = tau1 * a00 + tau2 * a01;
+            const C f00 = a00 - sr0, f01 = a01 - sr0 * v2c;         // H[k, k], H[k, k+1]: final for this sweep
+            const bool last = (k == iend - 1);
+            {
+                const bool l0 = lane == 0;
+                const uint32_t re = ring32 + (uint32_t)sizeof(ZOp) * (uint32_t)((sidx & 1) * cap + cnt);
+                sts_2i_if(re, (int)ZOP_REFL, k, l0 && wantZ);
+                sts_c64_if(re + 16, tau1, l0 && wantZ);
+                sts_c64_if(re + 32, v2, l0 && wantZ);
+                const uint32_t akm = ak - ES * (uint32_t)(k - 1 + EX);
+                const bool sub = l0 && (k > kf || store_sub);
+                sts_c64_if(akm + kb, mk_cx<R>(beta, zero), sub);
+                sts_c64_if(akm + kb + ES, mk_cx<R>(zero, zero), sub);
+                sts_c64_if(ak + kb, f00, l0);
+                sts_c64_if(ak1 + kb, f01, l0 && !last);
+            }
+            cnt += 1;
+            // ---- reflector k+1 (straight-line; the general routine only for out-of-range / degenerate input) ----
+            C t1n, v2n;
+            R betan;
+            bool ok;
+            {
+                const double a = n_v0.re, b = n_v0.im, cc = n_v1.re, dd = n_v1.im;
+                const double q = fma(a, a, b * b) + fma(cc, cc, dd * dd);
+                // q in [2^-900, 2^900]; tail and Im(alpha) not all exactly zero (src/householder.jl:67-69)
+                const unsigned tz = ((unsigned)(__double2hiint(cc) | __double2hiint(dd) | __double2hiint(b)) << 1) |
+                                    (unsigned)(__double2loint(cc) | __double2loint(dd) | __double2loint(b));
+                ok = q_exp_in(q, 1023u - 900u, 1023u + 900u) && (tz != 0u);
+                double yr;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(yr) : "d"(q));
+                const double qy = q * yr;
+                const double e = fma(-qy, yr, 1.0);
+                const double cf = fma(e, 0.375, 0.5);
+                yr = fma(yr * e, cf, yr);                 // 1/sqrt(q)
+                const double sq = q * yr;
+                const double rr = fma(-sq, sq, q);
+                const double nrm = fma(0.5 * yr, rr, sq);  // sqrt(q)
+                betan = -copysign(nrm, a);
+                double rb = -copysign(yr, a);              // ~ 1/beta
+                rb = fma(rb, fma(-betan, rb, 1.0), rb);
+                t1n = mk_cx<R>((betan - a) * rb, -b * rb);
+                const double amb = a - betan;
+                const double rm = fast_rcp(fma(amb, amb, b * b));
+                const double tr = amb * rm, ti = -b * rm;
+                v2n = mk_cx<R>(cc * tr - dd * ti, cc * ti + dd * tr);
+            }
+            // ---- bulk items: reflector k on the owned columns (left) / rows (right, conjugated) ----
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const C x = c[s];
+                const C ss = tau1c * x + tau2 * y[s];
+                C st = x - ss;
+                st.im = flip_if(st.im, sg[s]);
+                sts_c64_if(sa[s], st, act[s]);
+                const C nc = y[s] - ss * v2;
+                c[s].re = act[s] ? nc.re : c[s].re;
+                c[s].im = act[s] ? nc.im : c[s].im;
+                sts_c64_if(sa[s] + ES, nc, own2[s]);   // column k+2 enters the register block next step
+            }
+            if (last) {
+                f_sub = n_v0;
+                f_diag = n_d00;
+                f_sup = f01;
+                break;
+            }
+            if (!ok) {
+                v0 = n_v0;
+                v1 = n_v1;
+                t1n = reflector_cplx2_generic<R>(v0, v1);
+                betan = v0.re;
+                v2n = v1;
+            }
+            tau1 = t1n;
+            v2 = v2n;
+            beta = betan;
+            d00 = n_d00;
+            d10 = n_d10;
+            ak = ak1;
+        }
+#ifdef GS_QR_PROFILE
+        prof[3] += clock64() - tp2;
+#endif
+        stp[1] += napplied + (unsigned)(iend - kf);
+        // ---- write back what is still in registers after the last step (k = iend-1); the unit-modulus factor that makes
+        //      H[iend, iend-1] real (src/GenericSchur.jl:486-500) is applied on the way: row iend right of the diagonal
+        //      gets conj(t), column iend above it gets t — both are a multiplication by conj(t) of what the lanes hold ----
+        C tph = mk_cx<R>(1.0, zero);
+        R fsr = f_sub.re;
+        const bool fix = f_sub.im != zero;
+        if (fix) {
+            fsr = c_abs_q(f_sub);
+            const R ri = q_rcp(fsr);
+            tph = mk_cx<R>(f_sub.re * ri, f_sub.im * ri);
+            emit_scale_c(iend, iend, tph);
+        }
+        const C tphc = cconj(tph);
+        __syncwarp();
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+            const int j = lane + 1 + 32 * s;
+            C v = c[s];
+            if (fix) v = v * tphc;
+            if (j >= iend + 1 && j <= n) HH(iend, j) = v;
+            if (j <= iend - 2) HH(j, iend) = cconj(v);
+        }
+        if (lane == 0) {
+            HH(iend, iend - 1) = mk_cx<R>(fsr, zero);
+            HH(iend, iend) = f_diag;
+            HH(iend - 1, iend) = fix ? f_sup * tph : f_sup;
+        }
+        __syncwarp();
+    }
+
     GS_DEV int qr_complex(int maxiter, unsigned* st) {
         stp = st;
+#ifdef GS_QR_PROFILE
+        prof[0] = prof[1] = prof[2] = prof[3] = 0;
+        const long long tq0 = clock64();
+#endif
         const R zero = r_const<R>(0.0), half = r_const<R>(0.5), threeq = r_const<R>(0.75);
         const R ulp = rtraits<R>::eps();
         const R smallnum = r_safemin<R>() * (r_const<R>((double)n) / ulp);
@@ -497,28 +848,38 @@ template <class T, int CPL> struct FastSolver {
                     st[2] += 1;
                 } else {
                     t = HH(iend, iend);
-                    C u = c_sqrt(HH(iend - 1, iend)) * c_sqrt(HH(iend, iend - 1));
+                    C u = c_sqrt_q(HH(iend - 1, iend)) * c_sqrt_q(HH(iend, iend - 1));
                     R s = abs1(u);
                     if (s != zero) {
                         C x = half * (HH(iend - 1, iend - 1) - t);
                         R sx = abs1(x);
                         s = r_max(s, sx);
-                        C xs = mk_cx<R>(x.re / s, x.im / s), us = mk_cx<R>(u.re / s, u.im / s);
-                        C y = s * c_sqrt(xs * xs + us * us);
+                        const R rs = q_rcp(s);
+                        C xs = mk_cx<R>(x.re * rs, x.im * rs), us = mk_cx<R>(u.re * rs, u.im * rs);
+                        C y = s * c_sqrt_q(xs * xs + us * us);
                         if (sx > zero) {
-                            if ((x.re / sx) * y.re + (x.im / sx) * y.im < zero) y = -y;
+                            const R rsx = q_rcp(sx);
+                            if ((x.re * rsx) * y.re + (x.im * rsx) * y.im < zero) y = -y;
                         }
-                        t = t - u * (u / (x + y));
+                        t = t - u * c_div_q(u, x + y);
                     }
                 }
                 st[0] += 1;
-                sweep_complex(t, istart, iend);
+                if constexpr (sizeof(R) == 8) sweep_complex_pipelined(t, istart, iend);
+                else sweep_complex(t, istart, iend);
                 // hand the sweep's reflectors to the Z-warp
                 publish(0);
                 begin_buffer();
             }
         }
         st[3] = it;
+#ifdef GS_QR_PROFILE
+        prof[0] = clock64() - tq0;
+        st[0] = (unsigned)(prof[0] >> 6);   // total
+        st[2] = (unsigned)(prof[1] >> 6);   // waiting for the Z-warp to release a ring buffer
+        st[3] = (unsigned)(prof[3] >> 6);   // step loops
+        // st[1] keeps the number of steps
+#endif
         finish_ring();
         return 0;
     }
@@ -847,7 +1208,64 @@ template <class T, int CPL> struct FastSolver {
             int i = 0;
             while (i < count) {
                 const int op = ops[i].op;
-                if constexpr (CPLX) {
+                if constexpr (CPLX && sizeof(R) == 8 && GS_ZRUN > 0) {
+                    if (op == ZOP_REFL) {
+                        // A run of up to ZRUN reflectors on consecutive columns k, k+1, ...: all ZRUN+1 columns are
+                        // fetched from L2 up front (one latency per run instead of one per reflector), the reflectors
+                        // are applied from registers, then the columns go back.
+                        constexpr int ZRUN = GS_ZRUN > 0 ? GS_ZRUN : 1;
+                        const int k = ops[i].k;
+                        int m = 1;
+                        while (m < ZRUN && i + m < count && ops[i + m].op == ZOP_REFL && ops[i + m].k == k + m) m += 1;
+                        C z[ZRUN + 1][CPL];
+#pragma unroll
+                        for (int t = 0; t <= ZRUN; ++t) {
+                            if (t <= m) {
+#pragma unroll
+                                for (int s = 0; s < CPL; ++s) {
+                                    const int r = lane + 1 + 32 * s;
+                                    if (r <= n) z[t][s] = ZZ(r, k + t);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int t = 0; t < ZRUN; ++t) {
+                            if (t < m) {
+                                const C tau1 = mk_cx<R>(ops[i + t].a[0], ops[i + t].a[1]);
+                                const C v2 = mk_cx<R>(ops[i + t].a[2], ops[i + t].a[3]);
+                                const C v2c = cconj(v2);
+                                const R tau2 = tau1.re * v2.re - tau1.im * v2.im;
+#pragma unroll
+                                for (int s = 0; s < CPL; ++s) {
+                                    const C ss = tau1 * z[t][s] + tau2 * z[t + 1][s];
+                                    z[t][s] = z[t][s] - ss;
+                                    z[t + 1][s] = z[t + 1][s] - ss * v2c;
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int t = 0; t <= ZRUN; ++t) {
+                            if (t <= m) {
+#pragma unroll
+                                for (int s = 0; s < CPL; ++s) {
+                                    const int r = lane + 1 + 32 * s;
+                                    if (r <= n) ZZ(r, k + t) = z[t][s];
+                                }
+                            }
+                        }
+                        i += m;
+                    } else {   // ZOP_SCALE
+                        const C t = mk_cx<R>(ops[i].a[0], ops[i].a[1]);
+                        for (int j = ops[i].k; j <= ops[i].k2; ++j) {
+#pragma unroll
+                            for (int s = 0; s < CPL; ++s) {
+                                const int r = lane + 1 + 32 * s;
+                                if (r <= n) ZZ(r, j) = ZZ(r, j) * t;
+                            }
+                        }
+                        i += 1;
+                    }
+                } else if constexpr (CPLX) {
                     if (op == ZOP_REFL) {
                         int k = ops[i].k;
                         C z0[CPL], zn[CPL];
@@ -985,6 +1403,23 @@ template <class T, int CPL> struct FastSolver {
 //   in:  A_b = H_b (upper Hessenberg), Z_b = Q_b (or the caller's Z with GSCHUR_FLAG_HESS_INPUT), scratch (scale info)
 //   out: A_b <- T_b, Z_b <- Z_b * (accumulated reflectors), w, info, stats
 // =================================================================================================
+// The Z-warp's code lives in its own (non-inlined) function: its register allocation — the run of ZRUN+1 columns held
+// in registers — must not leak into the H-warp's step loop, which is compiled at the same per-thread register cap.
+template <class T, int CPL>
+__device__ __noinline__ void z_consumer_entry(int n, int lane, int ldz, T* Z, typename FastSolver<T, CPL>::ZOp* ring,
+                                              zring_hdr* hdr, int cap) {
+    FastSolver<T, CPL> F;
+    F.n = n;
+    F.lane = lane;
+    F.ldz = ldz;
+    F.Z = Z;
+    F.ring = ring;
+    F.hdr = hdr;
+    F.cap = cap;
+    F.wantZ = true;
+    F.z_consumer();
+}
+
 template <class T, int CPL> struct fast_smem_layout {
     typedef typename etraits<T>::real R;
     typedef smem_layout<T> L;
@@ -1004,7 +1439,9 @@ template <class T, int CPL> struct fast_smem_layout {
 
 // register budget: small real tiles are occupancy-bound (cap at 64 registers -> 16 CTAs/SM), the others shared-memory-bound
 template <class T, int CPL> struct qr_min_blocks {
-    static constexpr int value = (!etraits<T>::is_complex && CPL == 1 && sizeof(T) == 8) ? 16 : 1;
+    static constexpr int value = (!etraits<T>::is_complex && CPL == 1 && sizeof(T) == 8) ? 16
+                                 : (etraits<T>::is_complex && sizeof(T) == 16 && CPL == 2) ? 6   // 64x64 ComplexF64: six CTAs/SM fit in shared memory
+                                 : 1;
 };
 
 template <class T, int CPL>
@@ -1018,11 +1455,26 @@ __global__ void __launch_bounds__(64, qr_min_blocks<T, CPL>::value) gschur_qr_ke
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n;
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int lane = tid & 31;
     __shared__ long long s_next;
     __shared__ int s_info;
     __shared__ unsigned s_stats[4];
+    __shared__ unsigned s_w0;
     const bool wantZ = (p.Z != nullptr);
+    // Role assignment.  Warp schedulers are picked by the hardware warp slot (slot mod 4) and a 64-thread CTA takes two
+    // consecutive slots, so with a fixed "warp 0 = H-warp" every H-warp of the SM would sit on two of the four
+    // schedulers (measured: the FP64 pipes of those two saturate while the other two idle).  The H role therefore
+    // alternates between the CTA's two warps with bit 2 of the slot number: H-warps land on all four schedulers.
+    int warp = tid >> 5;
+    if (!(p.flags & F_FIXED_ROLES)) {
+        if (tid == 0) {
+            unsigned w;
+            asm volatile("mov.u32 %0, %%warpid;" : "=r"(w));
+            s_w0 = w;
+        }
+        __syncthreads();
+        warp ^= (int)((s_w0 >> 2) & 1u);   // role index: 0 = H-warp, 1 = Z-warp
+    }
 
     FS F;
     F.n = n;
@@ -1077,7 +1529,7 @@ __global__ void __launch_bounds__(64, qr_min_blocks<T, CPL>::value) gschur_qr_ke
                     s_stats[3] = st[3];
                 }
             } else if (wantZ) {
-                F.z_consumer();
+                z_consumer_entry<T, CPL>(n, lane, F.ldz, F.Z, F.ring, F.hdr, F.cap);
             }
             __syncthreads();
             info = s_info;
@@ -1175,8 +1627,11 @@ template <class T, int CPL> int launch_fast(const BatchedParams& p_in, int dev_s
         *err = "qr kernel does not fit on an SM";
         rc = -3;
     } else {
+        static const int cap_per_sm = std::getenv("GSCHUR_QR_CTAS_PER_SM") ? std::atoi(std::getenv("GSCHUR_QR_CTAS_PER_SM")) : 0;
+        if (cap_per_sm > 0 && cap_per_sm < per_sm) per_sm = cap_per_sm;   // profiling knob: occupancy sweep
         long long grid = (long long)per_sm * dev_sms;
         if (grid > p.batch) grid = p.batch;
+        if (std::getenv("GSCHUR_QR_FIXED_ROLES")) p.flags |= F_FIXED_ROLES;   // profiling knob
         kern<<<(unsigned)grid, 64, smem, stream>>>(p);
         note_launch();
         stage_timing_mark(2, stream);

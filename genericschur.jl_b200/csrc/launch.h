@@ -22,7 +22,7 @@ struct BatchedParams {
 };
 
 enum { MODE_SCHUR = 0, MODE_HESSENBERG = 1 };
-enum { F_HESS_INPUT = 0x2u, F_CHECK_SUBDIAG = 0x4u };
+enum { F_HESS_INPUT = 0x2u, F_CHECK_SUBDIAG = 0x4u, F_FIXED_ROLES = 0x100u };
 
 // every kernel launch of the library is counted (gschur_cuda_launch_count)
 void note_launch();

@@ -196,6 +196,21 @@ GS_DEV void pow2_scales(double w, double& down, double& up) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Guarded fast versions for the per-sweep scalar bookkeeping (deflation test, shift, start-row search).  Inside
+// a safe exponent window they use the MUFU + Newton primitives above (results within ~1 ulp of the IEEE ones, no
+// slow-path branches); outside they fall back to IEEE division / sqrt.  The double-double overloads are the
+// exact operations.
+// ------------------------------------------------------------------------------------------------
+GS_DEV bool q_exp_in(double a, unsigned lo, unsigned hi) {   // biased exponent of a in [lo, hi]
+    const unsigned e = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
+    return (e - lo) <= (hi - lo);
+}
+GS_DEV double q_rcp(double a) { return q_exp_in(a, 40u, 2000u) ? fast_rcp(a) : 1.0 / a; }
+GS_DEV dd_t q_rcp(const dd_t& a) { return mk_dd(1.0) / a; }
+GS_DEV double q_sqrt(double a) { return (a > 0.0 && q_exp_in(a, 40u, 2000u)) ? fast_sqrt(a) : __dsqrt_rn(a); }
+GS_DEV dd_t q_sqrt(const dd_t& a) { return dd_sqrt(a); }
+
+// ------------------------------------------------------------------------------------------------
 // complex
 // ------------------------------------------------------------------------------------------------
 template <class R> struct __align__(16) cx {
@@ -253,6 +268,34 @@ template <class R> GS_DEV cx<R> c_sqrt(const cx<R>& z) {
     }
     return mk_cx<R>(xi * sm, eta * sm);
 }
+
+// guarded fast complex square root / division / modulus (Float64); generic fallbacks otherwise
+GS_DEV cx<double> c_sqrt_q(const cx<double>& z) {
+    const double m = fmax(fabs(z.re), fabs(z.im));
+    if (!q_exp_in(m, 1023u - 400u, 1023u + 400u)) return c_sqrt(z);   // also zero / inf / nan
+    const double h = fast_sqrt(fma(z.re, z.re, z.im * z.im));
+    const double rho = fast_sqrt((h + fabs(z.re)) * 0.5);
+    double xi = rho, eta = (z.im * fast_rcp(rho)) * 0.5;
+    if (z.re < 0.0) {
+        xi = fabs(eta);
+        eta = copysign(rho, z.im);
+    }
+    return mk_cx<double>(xi, eta);
+}
+GS_DEV cx<dd_t> c_sqrt_q(const cx<dd_t>& z) { return c_sqrt(z); }
+GS_DEV cx<double> c_div_q(const cx<double>& a, const cx<double>& b) {
+    const double m = fmax(fabs(b.re), fabs(b.im));
+    if (!q_exp_in(m, 1023u - 400u, 1023u + 400u)) return a / b;
+    const double rd = fast_rcp(fma(b.re, b.re, b.im * b.im));
+    return mk_cx<double>(fma(a.re, b.re, a.im * b.im) * rd, fma(a.im, b.re, -a.re * b.im) * rd);
+}
+GS_DEV cx<dd_t> c_div_q(const cx<dd_t>& a, const cx<dd_t>& b) { return a / b; }
+GS_DEV double c_abs_q(const cx<double>& a) {
+    const double m = fmax(fabs(a.re), fabs(a.im));
+    if (!q_exp_in(m, 1023u - 400u, 1023u + 400u)) return c_abs(a);
+    return fast_sqrt(fma(a.re, a.re, a.im * a.im));
+}
+GS_DEV dd_t c_abs_q(const cx<dd_t>& a) { return c_abs(a); }
 
 // element-type traits
 template <class T> struct etraits;
