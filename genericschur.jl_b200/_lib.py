@@ -8,7 +8,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgschur_cuda.so")
+LIB_PATH = os.environ.get("GSCHUR_CUDA_LIB", os.path.join(_HERE, "libgschur_cuda.so"))   # override: development builds
 
 F64, C64, DD, CDD = 0, 1, 2, 3
 FLAG_DEVICE_PTRS = 0x1

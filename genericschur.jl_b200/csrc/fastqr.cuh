@@ -27,6 +27,12 @@
 #include <cstdlib>
 #include "gehrd.cuh"
 
+#ifndef GS_QR_MINB_F64_1
+#define GS_QR_MINB_F64_1 12  // 32x32 Float64: CTAs per SM the register budget is sized for
+#endif
+#ifndef GS_QR_MINB_F64_2
+#define GS_QR_MINB_F64_2 8   // 64x64 Float64
+#endif
 #ifndef GS_ZRUN
 #define GS_ZRUN 8
 #endif
@@ -127,6 +133,13 @@ GS_DEV void sts_2i_if(uint32_t a, int x, int y, bool p) {
                  : "memory");
 }
 
+GS_DEV void sts_f64_if(uint32_t a, double v, bool p) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q st.shared.f64 [%0], %1; }" ::"r"(a), "d"(v), "r"((int)p) : "memory");
+}
+GS_DEV void lds_f64_if(double& v, uint32_t a, bool p) {
+    asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q ld.shared.f64 %0, [%1]; }" : "+d"(v) : "r"(a), "r"((int)p));
+}
+
 template <class T, int CPL> struct FastSolver {
     typedef typename etraits<T>::real R;
     typedef cx<R> C;
@@ -189,23 +202,23 @@ template <class T, int CPL> struct FastSolver {
             R ab = r_max(h, o), ba = r_min(h, o);
             R d1 = r_abs(Hkk), d2 = r_abs(Hk1 - Hkk);
             R aa = r_max(d1, d2), bb = r_min(d1, d2);
-            R s = aa + bb;   // as the reference has it (src/GenericSchur.jl:586)
-            if (ba * (ab / s) <= r_max(smallnum, eps * (bb * (aa / s)))) return true;
+            R rs = q_rcp(aa + bb);   // s = aa + bb as the reference has it (src/GenericSchur.jl:586)
+            if (ba * (ab * rs) <= r_max(smallnum, eps * (bb * (aa * rs)))) return true;
         }
         return false;
     }
     GS_DEV void first_column_r(int m, const R& r1r, const R& r1i, const R& r2r, const R& r2i, R& v0, R& v1, R& v2) {
         R hmm = HH(m, m);
         R H21s = HH(m + 1, m);
-        R s = r_abs(hmm - r2r) + r_abs(r2i) + r_abs(H21s);
-        H21s = H21s / s;
-        v0 = H21s * HH(m, m + 1) + (hmm - r1r) * ((hmm - r2r) / s) - r1i * (r2i / s);
+        R s = q_rcp(r_abs(hmm - r2r) + r_abs(r2i) + r_abs(H21s));
+        H21s = H21s * s;
+        v0 = H21s * HH(m, m + 1) + (hmm - r1r) * ((hmm - r2r) * s) - r1i * (r2i * s);
         v1 = H21s * (hmm + HH(m + 1, m + 1) - r1r - r2r);
         v2 = H21s * HH(m + 2, m + 1);
-        s = r_abs(v0) + r_abs(v1) + r_abs(v2);
-        v0 = v0 / s;
-        v1 = v1 / s;
-        v2 = v2 / s;
+        s = q_rcp(r_abs(v0) + r_abs(v1) + r_abs(v2));
+        v0 = v0 * s;
+        v1 = v1 * s;
+        v2 = v2 * s;
     }
 
     // ------------------------------------------------------------------------------------------------
@@ -1064,8 +1077,246 @@ template <class T, int CPL> struct FastSolver {
     }
 
 
+    // ================================================================================================
+    // real double shift, software-pipelined (Float64) — the same construction as sweep_complex_pipelined: the 3x3
+    // diagonal block (plus the sub-diagonal entry below it) is replicated in registers, every other entry of rows
+    // k..k+2 (columns >= k+3) and of columns k..k+2 (rows <= k-1) is a bulk item with two running entries per owned
+    // index, and one loop iteration applies reflector k to the bulk items while it forms reflector k+1 from the
+    // register block.  Arithmetic per entry as in src/GenericSchur.jl:906-925.
+    // ================================================================================================
+    GS_DEV void sweep_real_pipelined(const R& r1r, const R& r1i, const R& r2r, const R& r2i, int istart, int iend) {
+        static_assert(sizeof(T) == 8, "Float64 only");
+        const R zero = 0.0, one = 1.0;
+        const R eps = rtraits<R>::eps();
+        int mx = 0;
+        for (int base = iend - 2; base >= istart + 1 && !mx; base -= 32) {
+            int m = base - lane;
+            bool hit = false;
+            if (m >= istart + 1) {
+                R a0, a1, a2;
+                first_column_r(m, r1r, r1i, r2r, r2i, a0, a1, a2);
+                hit = r_abs(HH(m, m - 1)) * (r_abs(a1) + r_abs(a2)) <=
+                      eps * r_abs(a0) * (r_abs(HH(m - 1, m - 1)) + r_abs(HH(m, m)) + r_abs(HH(m + 1, m + 1)));
+            }
+            unsigned msk = __ballot_sync(0xffffffffu, hit);
+            if (msk) mx = base - (__ffs(msk) - 1);
+        }
+        if (!mx) mx = istart;
+        R v0, v1, v2;
+        first_column_r(mx, r1r, r1i, r2r, r2i, v0, v1, v2);
+        constexpr uint32_t ES = (uint32_t)sizeof(T);
+        const uint32_t hb = smem_u32(H);
+        uint32_t ca[CPL], ib[CPL];
+        int jl[CPL];
+        R c1[CPL], c2[CPL];   // running entries: left item H[k, j], H[k+1, j];  right item H[j, k], H[j, k+1]
+        uint32_t ak = hb + ES * (uint32_t)(colbase(mx) - 1);   // column k, "row 0"
+        {
+            const uint32_t ak1 = ak + ES * (uint32_t)(mx + EX);
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const int j = lane + 1 + 32 * s;
+                const bool valid = j <= n;
+                jl[s] = valid ? j : -(1 << 28);
+                ca[s] = hb + ES * (uint32_t)(colbase(valid ? j : 1) - 1);
+                ib[s] = ES * (uint32_t)(valid ? j : 1);
+                c1[s] = zero;
+                c2[s] = zero;
+                if (jl[s] >= mx + 3) {
+                    c1[s] = lds_e<T>(ca[s] + ES * mx);
+                    c2[s] = lds_e<T>(ca[s] + ES * (mx + 1));
+                } else if (j <= mx - 1) {
+                    c1[s] = lds_e<T>(ak + ib[s]);
+                    c2[s] = lds_e<T>(ak1 + ib[s]);
+                }
+            }
+        }
+        // register block: columns k and k+1 of rows k..k+2 are carried, column k+2 is picked up at the top of each step
+        R b00 = HH(mx, mx), b10 = HH(mx + 1, mx), b20 = HH(mx + 2, mx);
+        R b01 = HH(mx, mx + 1), b11 = HH(mx + 1, mx + 1), b21 = HH(mx + 2, mx + 1);
+        R tau1 = reflector_real_small(v0, v1, v2, 3);
+        R beta = v0;
+        R L10 = zero, L20 = zero, L11 = zero, L21 = zero, L12 = zero, L22 = zero, L01 = zero, L02 = zero;
+        const int capz = wantZ ? cap : 0x7fffffff;
+        const uint32_t ring32 = smem_u32(ring);
+#ifdef GS_QR_PROFILE
+        const long long tp2 = clock64();
+#endif
+        for (int k = mx;; ++k) {
+            if (cnt == capz) {
+                publish(0);
+                begin_buffer();
+            }
+            __syncwarp();
+            const uint32_t kb = ES * (uint32_t)k;
+            const uint32_t ak1 = ak + ES * (uint32_t)(k + EX);        // column k+1
+            const uint32_t ak2 = ak1 + ES * (uint32_t)(k + 1 + EX);   // column k+2
+            // ---- loads: column k+2 of the block (rows k..k+3); third entry of every bulk item ----
+            const R b02 = lds_e<T>(ak2 + kb), b12 = lds_e<T>(ak2 + kb + ES), b22 = lds_e<T>(ak2 + kb + 2 * ES);
+            R e3 = zero;
+            if (k + 3 <= iend) e3 = lds_e<T>(ak2 + kb + 3 * ES);
+            bool act[CPL], own3[CPL];
+            uint32_t sa[CPL];
+            R y[CPL];
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const int j = lane + 1 + 32 * s;
+                const bool isL = jl[s] >= k + 3;
+                const bool isR = j <= k - 1;
+                act[s] = isL || isR;
+                own3[s] = jl[s] == k + 3;
+                sa[s] = isR ? ak + ib[s] : ca[s] + kb;                  // inactive lanes: a harmless address
+                const uint32_t ya = isR ? ak2 + ib[s] : sa[s] + 2 * ES;
+                lds_f64_if(c1[s], sa[s], j == k - 1);                   // row k-1 left the register block
+                lds_f64_if(c2[s], ak1 + ib[s], j == k - 1);
+                y[s] = lds_e<T>(ya);
+            }
+            const R tau2 = tau1 * v1, tau3 = tau1 * v2;
+            // ---- chain: rows k..k+2 of columns k..k+2 (left), then columns k..k+2 of rows k..k+3 (right) ----
+            const R s0 = fma(v2, b20, fma(v1, b10, b00));
+            const R a00 = fma(-s0, tau1, b00), a10 = fma(-s0, tau2, b10), a20 = fma(-s0, tau3, b20);
+            const R s1 = fma(v2, b21, fma(v1, b11, b01));
+            const R a01 = fma(-s1, tau1, b01), a11 = fma(-s1, tau2, b11), a21 = fma(-s1, tau3, b21);
+            const R s2 = fma(v2, b22, fma(v1, b12, b02));
+            const R a02 = fma(-s2, tau1, b02), a12 = fma(-s2, tau2, b12), a22 = fma(-s2, tau3, b22);
+            const R t1 = fma(v2, a12, fma(v1, a11, a10));
+            const R f10 = fma(-t1, tau1, a10), f11 = fma(-t1, tau2, a11), f12 = fma(-t1, tau3, a12);   // row k+1
+            const R t2 = fma(v2, a22, fma(v1, a21, a20));
+            const R f20 = fma(-t2, tau1, a20), f21 = fma(-t2, tau2, a21), f22 = fma(-t2, tau3, a22);   // row k+2
+            const R t3 = v2 * e3;
+            const R f30 = -t3 * tau1, f31 = -t3 * tau2, f32 = fma(-t3, tau3, e3);                      // row k+3
+            const R t0 = fma(v2, a02, fma(v1, a01, a00));
+            const R f00 = fma(-t0, tau1, a00), f01 = fma(-t0, tau2, a01), f02 = fma(-t0, tau3, a02);   // row k: final
+            const bool last = (k == iend - 2);
+            {
+                const bool l0 = lane == 0;
+                const uint32_t re = ring32 + (uint32_t)sizeof(ZOp) * (uint32_t)((sidx & 1) * cap + cnt);
+                sts_2i_if(re, (int)ZOP_REFL3, k, l0 && wantZ);
+                sts_f64_if(re + 8, tau1, l0 && wantZ);
+                sts_f64_if(re + 16, v1, l0 && wantZ);
+                sts_f64_if(re + 24, v2, l0 && wantZ);
+                const uint32_t akm = ak - ES * (uint32_t)(k - 1 + EX);
+                const bool sub = l0 && (k > mx);
+                sts_f64_if(akm + kb, beta, sub);
+                sts_f64_if(akm + kb + ES, zero, sub);
+                sts_f64_if(akm + kb + 2 * ES, zero, sub);
+                if (l0 && k == mx && mx > istart) sts_e<T>(akm + kb, lds_e<T>(akm + kb) * (one - tau1));
+                sts_f64_if(ak + kb, f00, l0);
+                sts_f64_if(ak1 + kb, f01, l0);
+                sts_f64_if(ak2 + kb, f02, l0);
+            }
+            cnt += 1;
+            // ---- reflector k+1 from (f10, f20, f30), straight-line (general routine only for out-of-range input) ----
+            R t1n, v1n, v2n, betan;
+            bool ok;
+            {
+                const double q = fma(f10, f10, fma(f20, f20, f30 * f30));
+                const unsigned tz = ((unsigned)(__double2hiint(f20) | __double2hiint(f30)) << 1) |
+                                    (unsigned)(__double2loint(f20) | __double2loint(f30));
+                ok = q_exp_in(q, 1023u - 900u, 1023u + 900u) && (tz != 0u);
+                double yr;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(yr) : "d"(q));
+                const double qy = q * yr;
+                const double e = fma(-qy, yr, 1.0);
+                const double cf = fma(e, 0.375, 0.5);
+                yr = fma(yr * e, cf, yr);                 // 1/sqrt(q)
+                const double sq = q * yr;
+                const double rr = fma(-sq, sq, q);
+                const double nrm = fma(0.5 * yr, rr, sq);  // sqrt(q)
+                betan = -copysign(nrm, f10);
+                double rb = -copysign(yr, f10);            // ~ 1/beta
+                rb = fma(rb, fma(-betan, rb, 1.0), rb);
+                t1n = (betan - f10) * rb;
+                const double tt = fast_rcp(f10 - betan);
+                v1n = f20 * tt;
+                v2n = f30 * tt;
+            }
+            // ---- bulk items ----
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const R ss = fma(v2, y[s], fma(v1, c2[s], c1[s]));
+                sts_f64_if(sa[s], fma(-ss, tau1, c1[s]), act[s]);
+                const R n1 = fma(-ss, tau2, c2[s]), n2 = fma(-ss, tau3, y[s]);
+                c1[s] = act[s] ? n1 : c1[s];
+                c2[s] = act[s] ? n2 : c2[s];
+                sts_f64_if(sa[s] + ES, n1, own3[s]);        // column k+3 enters the register block next step
+                sts_f64_if(sa[s] + 2 * ES, n2, own3[s]);
+            }
+            if (last) {
+                L10 = f10; L20 = f20; L11 = f11; L21 = f21; L12 = f12; L22 = f22; L01 = f01; L02 = f02;
+                break;
+            }
+            if (!ok) {
+                R w0 = f10, w1 = f20, w2 = f30;
+                t1n = reflector_real_small(w0, w1, w2, 3);
+                betan = w0;
+                v1n = w1;
+                v2n = w2;
+            }
+            tau1 = t1n;
+            v1 = v1n;
+            v2 = v2n;
+            beta = betan;
+            b00 = f11;
+            b10 = f21;
+            b20 = f31;
+            b01 = f12;
+            b11 = f22;
+            b21 = f32;
+            ak = ak1;
+        }
+#ifdef GS_QR_PROFILE
+        prof[3] += clock64() - tp2;
+#endif
+        // ---- last step: the two-row reflector at k = iend-1 (src/GenericSchur.jl:927-946), entirely on registers:
+        //      the lanes already hold rows iend-1, iend of their columns (left items) / columns iend-1, iend of their
+        //      rows (right items), the block and row iend-2 are replicated; everything is written back afterwards ----
+        {
+            const int k = iend - 1;
+            R w0 = L10, w1 = L20, w2 = zero;
+            const R t1 = reflector_real_small(w0, w1, w2, 2);
+            const R t2 = t1 * w1;
+            emit_r(ZOP_REFL2, k, t1, w1, zero);
+            // left on the block's columns
+            const R sa0 = L11 + w1 * L21, sa1 = L12 + w1 * L22;
+            const R g11 = L11 - sa0 * t1, g21 = L21 - sa0 * t2, g12 = L12 - sa1 * t1, g22 = L22 - sa1 * t2;
+            // right on rows iend-2, iend-1, iend
+            const R sr0 = L01 + w1 * L02, sr1 = g11 + w1 * g12, sr2 = g21 + w1 * g22;
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const int j = lane + 1 + 32 * s;
+                const R ss = c1[s] + w1 * c2[s];
+                const R n1 = c1[s] - ss * t1, n2 = c2[s] - ss * t2;
+                if (j >= iend + 1 && j <= n) {
+                    HH(iend - 1, j) = n1;
+                    HH(iend, j) = n2;
+                }
+                if (j <= iend - 3) {
+                    HH(j, iend - 1) = n1;
+                    HH(j, iend) = n2;
+                }
+            }
+            if (lane == 0) {
+                HH(k, k - 1) = w0;
+                HH(k + 1, k - 1) = zero;
+                HH(k - 1, k) = L01 - sr0 * t1;
+                HH(k - 1, k + 1) = L02 - sr0 * t2;
+                HH(k, k) = g11 - sr1 * t1;
+                HH(k, k + 1) = g12 - sr1 * t2;
+                HH(k + 1, k) = g21 - sr2 * t1;
+                HH(k + 1, k + 1) = g22 - sr2 * t2;
+            }
+            __syncwarp();
+        }
+        stp[1] += (unsigned)(iend - mx);
+    }
+
     GS_DEV int qr_real(int maxiter, unsigned* st) {
         stp = st;
+#ifdef GS_QR_PROFILE
+        prof[0] = prof[1] = prof[2] = prof[3] = 0;
+        const long long tq0 = clock64();
+#endif
         const R zero = r_const<R>(0.0);
         const R eps = rtraits<R>::eps();
         const R smallnum = rtraits<R>::floatmin() * (r_const<R>((double)n) / eps);
@@ -1121,13 +1372,14 @@ template <class T, int CPL> struct FastSolver {
                 R s = r_abs(H11) + r_abs(H12) + r_abs(H21) + r_abs(H22);
                 R r1r = zero, r2r = zero, r1i = zero, r2i = zero;
                 if (!(s == zero)) {
-                    H11 = H11 / s;
-                    H12 = H12 / s;
-                    H21 = H21 / s;
-                    H22 = H22 / s;
+                    const R rs = q_rcp(s);
+                    H11 = H11 * rs;
+                    H12 = H12 * rs;
+                    H21 = H21 * rs;
+                    H22 = H22 * rs;
                     R tr = (H11 + H22) * r_const<R>(0.5);
                     R d = (H11 - tr) * (H22 - tr) - H12 * H21;
-                    R rtd = r_sqrt(r_abs(d));
+                    R rtd = q_sqrt(r_abs(d));
                     if (d >= zero) {
                         r1r = tr * s;
                         r2r = r1r;
@@ -1146,7 +1398,8 @@ template <class T, int CPL> struct FastSolver {
                     }
                 }
                 st[0] += 1;
-                sweep_real(r1r, r1i, r2r, r2i, istart, iend);
+                if constexpr (sizeof(T) == 8) sweep_real_pipelined(r1r, r1i, r2r, r2i, istart, iend);
+                else sweep_real(r1r, r1i, r2r, r2i, istart, iend);
                 publish(0);
                 begin_buffer();
             }
@@ -1189,6 +1442,12 @@ template <class T, int CPL> struct FastSolver {
             iend = istart - 1;
         }
         st[3] = iter;
+#ifdef GS_QR_PROFILE
+        prof[0] = clock64() - tq0;
+        st[0] = (unsigned)(prof[0] >> 6);
+        st[2] = (unsigned)(prof[1] >> 6);
+        st[3] = (unsigned)(prof[3] >> 6);
+#endif
         finish_ring();
         return 0;
     }
@@ -1439,7 +1698,8 @@ template <class T, int CPL> struct fast_smem_layout {
 
 // register budget: small real tiles are occupancy-bound (cap at 64 registers -> 16 CTAs/SM), the others shared-memory-bound
 template <class T, int CPL> struct qr_min_blocks {
-    static constexpr int value = (!etraits<T>::is_complex && CPL == 1 && sizeof(T) == 8) ? 16
+    static constexpr int value = (!etraits<T>::is_complex && CPL == 1 && sizeof(T) == 8) ? GS_QR_MINB_F64_1
+                                 : (!etraits<T>::is_complex && CPL == 2 && sizeof(T) == 8) ? GS_QR_MINB_F64_2
                                  : (etraits<T>::is_complex && sizeof(T) == 16 && CPL == 2) ? 6   // 64x64 ComplexF64: six CTAs/SM fit in shared memory
                                  : 1;
 };
