@@ -25,7 +25,7 @@
 // reference, src/GenericSchur.jl:194-335, 374-504, 513-699, 837-952); only the schedule and the layout differ.
 #pragma once
 #include <cstdlib>
-#include "gehrd.cuh"
+#include "gehrd_split.cuh"
 
 #ifndef GS_QR_MINB_F64_1
 #define GS_QR_MINB_F64_1 12  // 32x32 Float64: CTAs per SM the register budget is sized for
@@ -691,14 +691,14 @@ template <class T, int CPL> struct FastSolver {
             const C tau1c = cconj(tau1), v2c = cconj(v2);
             // ---- chain: rows k, k+1 of columns k, k+1 (left), then columns k, k+1 of rows k..k+2 (right) ----
             const C ss0 = tau1c * d00 + tau2 * d10;
-            const C a00 = d00 - ss0, a10 = d10 - ss0 * v2;
+            const C a00 = d00 - ss0, a10 = e_fnma(ss0, v2, d10);
             const C ss1 = tau1c * d01 + tau2 * d11;
-            const C a01 = d01 - ss1, a11 = d11 - ss1 * v2;
+            const C a01 = d01 - ss1, a11 = e_fnma(ss1, v2, d11);
             const C sr1 = tau1 * a10 + tau2 * a11;
-            const C n_v0 = a10 - sr1, n_d00 = a11 - sr1 * v2c;      // H[k+1, k], H[k+1, k+1]
-            const C n_v1 = (-tau2) * e1, n_d10 = e1 + n_v1 * v2c;   // H[k+2, k] (the bulge), H[k+2, k+1]
+            const C n_v0 = a10 - sr1, n_d00 = e_fnma(sr1, v2c, a11);     // H[k+1, k], H[k+1, k+1]
+            const C n_v1 = (-tau2) * e1, n_d10 = e_fma(n_v1, v2c, e1);   // H[k+2, k] (the bulge), H[k+2, k+1]
             const C sr0 = tau1 * a00 + tau2 * a01;
-            const C f00 = a00 - sr0, f01 = a01 - sr0 * v2c;         // H[k, k], H[k, k+1]: final for this sweep
+            const C f00 = a00 - sr0, f01 = e_fnma(sr0, v2c, a01);         // H[k, k], H[k, k+1]: final for this sweep
             const bool last = (k == iend - 1);
             {
                 const bool l0 = lane == 0;
@@ -725,21 +725,25 @@ template <class T, int CPL> struct FastSolver {
                 const unsigned tz = ((unsigned)(__double2hiint(cc) | __double2hiint(dd) | __double2hiint(b)) << 1) |
                                     (unsigned)(__double2loint(cc) | __double2loint(dd) | __double2loint(b));
                 ok = q_exp_in(q, 1023u - 900u, 1023u + 900u) && (tz != 0u);
-                double yr;
-                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(yr) : "d"(q));
-                const double qy = q * yr;
-                const double e = fma(-qy, yr, 1.0);
+                double yr0;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(yr0) : "d"(q));
+                // The seed of 1/|alpha - beta|^2 is taken from the unrefined norm so that the second MUFU overlaps the
+                // refinement of the first; its one cubic Newton step below uses the final denominator.
+                const double amb0 = a + copysign(q * yr0, a);
+                double y0;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(fma(amb0, amb0, b * b)));
+                const double qy = q * yr0;
+                const double e = fma(-qy, yr0, 1.0);
                 const double cf = fma(e, 0.375, 0.5);
-                yr = fma(yr * e, cf, yr);                 // 1/sqrt(q)
-                const double sq = q * yr;
-                const double rr = fma(-sq, sq, q);
-                const double nrm = fma(0.5 * yr, rr, sq);  // sqrt(q)
+                const double yr = fma(yr0 * e, cf, yr0);   // 1/sqrt(q), one cubic step: 2^-22 -> below 1 ulp
+                const double nrm = q * yr;                 // sqrt(q) within ~1 ulp
                 betan = -copysign(nrm, a);
-                double rb = -copysign(yr, a);              // ~ 1/beta
-                rb = fma(rb, fma(-betan, rb, 1.0), rb);
+                const double rb = -copysign(yr, a);        // 1/beta
                 t1n = mk_cx<R>((betan - a) * rb, -b * rb);
-                const double amb = a - betan;
-                const double rm = fast_rcp(fma(amb, amb, b * b));
+                const double amb = a - betan;              // |amb| >= |beta|: no cancellation
+                const double den = fma(amb, amb, b * b);
+                const double e2 = fma(-den, y0, 1.0);
+                const double rm = fma(y0, fma(e2, e2, e2), y0);   // y0 (1 + e + e^2)
                 const double tr = amb * rm, ti = -b * rm;
                 v2n = mk_cx<R>(cc * tr - dd * ti, cc * ti + dd * tr);
             }
@@ -751,7 +755,7 @@ template <class T, int CPL> struct FastSolver {
                 C st = x - ss;
                 st.im = flip_if(st.im, sg[s]);
                 sts_c64_if(sa[s], st, act[s]);
-                const C nc = y[s] - ss * v2;
+                const C nc = e_fnma(ss, v2, y[s]);
                 c[s].re = act[s] ? nc.re : c[s].re;
                 c[s].im = act[s] ? nc.im : c[s].im;
                 sts_c64_if(sa[s] + ES, nc, own2[s]);   // column k+2 enters the register block next step
@@ -1498,7 +1502,7 @@ template <class T, int CPL> struct FastSolver {
                                 for (int s = 0; s < CPL; ++s) {
                                     const C ss = tau1 * z[t][s] + tau2 * z[t + 1][s];
                                     z[t][s] = z[t][s] - ss;
-                                    z[t + 1][s] = z[t + 1][s] - ss * v2c;
+                                    z[t + 1][s] = e_fnma(ss, v2c, z[t + 1][s]);
                                 }
                             }
                         }
@@ -1864,7 +1868,7 @@ template <class T, int CPL> int launch_fast(const BatchedParams& p_in, int dev_s
         e = cudaMemsetAsync(counter2, 0, sizeof(unsigned long long), stream);
         p.scratch = scratch;
         stage_timing_mark(0, stream);
-        int rc = launch_gehrd<T, 64>(p, dev_sms, stream, err);
+        int rc = launch_stage_a<T>(p, dev_sms, stream, err);
         if (rc) {
             cudaFreeAsync(scratch, stream);
             return rc;

@@ -342,6 +342,30 @@ GS_DEV double e_scale(double a, double s) { return a * s; }
 GS_DEV dd_t e_scale(const dd_t& a, const dd_t& s) { return a * s; }
 template <class R> GS_DEV cx<R> e_scale(const cx<R>& a, const R& s) { return mk_cx<R>(a.re * s, a.im * s); }
 
+// fused element multiply-adds: a b + c, c - a b, conj(a) b + c, c - a conj(b).  Float64 / ComplexF64: every product
+// term is contracted into an FMA (2 / 4 DFMA instead of DMUL + DFMA + DADD per component, and one rounding fewer);
+// the double-double kinds use their ordinary operators.
+template <class T> GS_DEV T e_fma(const T& a, const T& b, const T& c) { return a * b + c; }
+template <class T> GS_DEV T e_fnma(const T& a, const T& b, const T& c) { return c - a * b; }
+template <class T> GS_DEV T e_fma_cja(const T& a, const T& b, const T& c) { return cconj(a) * b + c; }
+template <class T> GS_DEV T e_fnma_cjb(const T& a, const T& b, const T& c) { return c - a * cconj(b); }
+GS_DEV double e_fma(double a, double b, double c) { return fma(a, b, c); }                 // a b + c
+GS_DEV double e_fnma(double a, double b, double c) { return fma(-a, b, c); }               // c - a b
+GS_DEV double e_fma_cja(double a, double b, double c) { return fma(a, b, c); }             // conj(a) b + c
+GS_DEV double e_fnma_cjb(double a, double b, double c) { return fma(-a, b, c); }           // c - a conj(b)
+GS_DEV cx<double> e_fma(const cx<double>& a, const cx<double>& b, const cx<double>& c) {
+    return mk_cx<double>(fma(a.re, b.re, fma(-a.im, b.im, c.re)), fma(a.re, b.im, fma(a.im, b.re, c.im)));
+}
+GS_DEV cx<double> e_fnma(const cx<double>& a, const cx<double>& b, const cx<double>& c) {
+    return mk_cx<double>(fma(-a.re, b.re, fma(a.im, b.im, c.re)), fma(-a.re, b.im, fma(-a.im, b.re, c.im)));
+}
+GS_DEV cx<double> e_fma_cja(const cx<double>& a, const cx<double>& b, const cx<double>& c) {
+    return mk_cx<double>(fma(a.re, b.re, fma(a.im, b.im, c.re)), fma(a.re, b.im, fma(-a.im, b.re, c.im)));
+}
+GS_DEV cx<double> e_fnma_cjb(const cx<double>& a, const cx<double>& b, const cx<double>& c) {
+    return mk_cx<double>(fma(-a.re, b.re, fma(-a.im, b.im, c.re)), fma(a.re, b.im, fma(-a.im, b.re, c.im)));
+}
+
 // warp shuffles for every scalar type
 GS_DEV double shfl_xor(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
 GS_DEV dd_t shfl_xor(const dd_t& v, int m) {
