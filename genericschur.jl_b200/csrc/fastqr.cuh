@@ -647,7 +647,8 @@ template <class T, int CPL> struct FastSolver {
         C tau1 = reflector_cplx2(v0, v1);
         R beta = v0.re;
         C v2 = v1;
-        C f_sub, f_diag, f_sup;   // H[iend, iend-1], H[iend, iend], H[iend-1, iend] after the last step
+        R tau2 = tau1.re * v2.re - tau1.im * v2.im;   // Re(tau1 v2); tau1 v2 is real because the reflector's tail is
+        C f_sub, f_diag;   // H[iend, iend-1], H[iend, iend] after the last step
         const int capz = wantZ ? cap : 0x7fffffff;
         const uint32_t ring32 = smem_u32(ring);
 #ifdef GS_QR_PROFILE
@@ -664,9 +665,13 @@ template <class T, int CPL> struct FastSolver {
             const uint32_t ak1 = ak + ES * (uint32_t)(k + EX);        // column k+1
             // ---- loads: column k+1 of the block; second entry of every bulk item ----
             const C d01 = lds_e<T>(ak1 + kb), d11 = lds_e<T>(ak1 + kb + ES);
-            C e1 = mk_cx<R>(zero, zero);
-            if (k + 2 <= iend) e1 = lds_e<T>(ak1 + kb + 2 * ES);
-            bool act[CPL], own2[CPL];
+            // the sub-diagonal is real (stage A, every bulge step and the end-of-sweep fix-up write (beta, 0)): only Re is read
+            R e1 = zero;
+            if (k + 2 <= iend) e1 = lds_e<R>(ak1 + kb + 2 * ES);
+            // Row k itself (j == k) is a right item too: its two entries are rows k of the block after the left update (a00,
+            // a01, known to every lane) — the owner lane takes them over from the chain below, stores H[k, k] and carries
+            // H[k, k+1] into the next step, so the chain does not have to finish that row.
+            bool act[CPL], own2[CPL], isD[CPL];
             unsigned sg[CPL];
             uint32_t sa[CPL];
             C y[CPL];
@@ -674,31 +679,49 @@ template <class T, int CPL> struct FastSolver {
             for (int s = 0; s < CPL; ++s) {
                 const int j = lane + 1 + 32 * s;
                 const bool isL = jl[s] >= k + 2;
-                const bool isR = j <= k - 1;
+                const bool isR = j <= k;
+                isD[s] = j == k;
                 act[s] = isL || isR;
                 own2[s] = jl[s] == k + 2;
                 sg[s] = isR ? 0x80000000u : 0u;
                 sa[s] = isR ? ak + ib[s] : ca[s] + kb;                  // inactive lanes: a harmless address
                 const uint32_t ya = isR ? ak1 + ib[s] : sa[s] + ES;
-                C xr = mk_cx<R>(c[s].re, -c[s].im);
-                lds_c64_if(xr, sa[s], j == k - 1);                      // row k-1 left the register block: H[k-1, k]
-                c[s].re = xr.re;
-                c[s].im = -xr.im;
                 y[s] = lds_e<T>(ya);
                 y[s].im = flip_if(y[s].im, sg[s]);
             }
-            const R tau2 = tau1.re * v2.re - tau1.im * v2.im;
             const C tau1c = cconj(tau1), v2c = cconj(v2);
             // ---- chain: rows k, k+1 of columns k, k+1 (left), then columns k, k+1 of rows k..k+2 (right) ----
             const C ss0 = tau1c * d00 + tau2 * d10;
             const C a00 = d00 - ss0, a10 = e_fnma(ss0, v2, d10);
             const C ss1 = tau1c * d01 + tau2 * d11;
             const C a01 = d01 - ss1, a11 = e_fnma(ss1, v2, d11);
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                c[s].re = isD[s] ? a00.re : c[s].re;
+                c[s].im = isD[s] ? -a00.im : c[s].im;
+                y[s].re = isD[s] ? a01.re : y[s].re;
+                y[s].im = isD[s] ? -a01.im : y[s].im;
+            }
             const C sr1 = tau1 * a10 + tau2 * a11;
-            const C n_v0 = a10 - sr1, n_d00 = e_fnma(sr1, v2c, a11);     // H[k+1, k], H[k+1, k+1]
-            const C n_v1 = (-tau2) * e1, n_d10 = e_fma(n_v1, v2c, e1);   // H[k+2, k] (the bulge), H[k+2, k+1]
-            const C sr0 = tau1 * a00 + tau2 * a01;
-            const C f00 = a00 - sr0, f01 = e_fnma(sr0, v2c, a01);         // H[k, k], H[k, k+1]: final for this sweep
+            // H[k+1, k] = a10 - sr1 is the head of the next reflector, i.e. the serial chain of the sweep.  v2 is the last
+            // thing the previous reflector produces, so the expression is regrouped to need it once, at the very end:
+            // a10 - sr1 = (1 - tau1) a10 - tau2 a11 = [(1 - tau1) d10 - tau2 d11] - v2 [(1 - tau1) ss0 - tau2 ss1].
+            // Measured on B200: -18 % stage-B time for n <= 32 (CPL = 1); +8 % for n = 64 (CPL = 2), where the extra live values
+            // collide with the 168-register cap that six CTAs per SM impose — so the regrouping is used for CPL = 1 only.
+#ifndef GS_QR_REGROUP_MAXCPL
+#define GS_QR_REGROUP_MAXCPL 1
+#endif
+            C n_v0;
+            if constexpr (CPL <= GS_QR_REGROUP_MAXCPL) {
+                const C omt = mk_cx<R>(1.0 - tau1.re, -tau1.im);
+                const C pv = omt * d10 - tau2 * d11, qv = omt * ss0 - tau2 * ss1;
+                n_v0 = e_fnma(v2, qv, pv);
+            } else {
+                n_v0 = a10 - sr1;
+            }
+            const C n_d00 = e_fnma(sr1, v2c, a11);   // H[k+1, k], H[k+1, k+1]
+            const R n_v1 = -tau2 * e1;                                         // H[k+2, k], the bulge: real
+            const C n_d10 = mk_cx<R>(fma(n_v1, v2.re, e1), -n_v1 * v2.im);    // H[k+2, k+1] = e1 + n_v1 conj(v2)
             const bool last = (k == iend - 1);
             {
                 const bool l0 = lane == 0;
@@ -710,20 +733,19 @@ template <class T, int CPL> struct FastSolver {
                 const bool sub = l0 && (k > kf || store_sub);
                 sts_c64_if(akm + kb, mk_cx<R>(beta, zero), sub);
                 sts_c64_if(akm + kb + ES, mk_cx<R>(zero, zero), sub);
-                sts_c64_if(ak + kb, f00, l0);
-                sts_c64_if(ak1 + kb, f01, l0 && !last);
             }
             cnt += 1;
             // ---- reflector k+1 (straight-line; the general routine only for out-of-range / degenerate input) ----
             C t1n, v2n;
-            R betan;
+            R betan, tau2n;
             bool ok;
             {
-                const double a = n_v0.re, b = n_v0.im, cc = n_v1.re, dd = n_v1.im;
-                const double q = fma(a, a, b * b) + fma(cc, cc, dd * dd);
+                const double a = n_v0.re, b = n_v0.im, cc = n_v1;
+                // the bulge entry n_v1 = -tau2 e1 is real (tau2 and the sub-diagonal are)
+                const double q = fma(a, a, fma(b, b, cc * cc));
                 // q in [2^-900, 2^900]; tail and Im(alpha) not all exactly zero (src/householder.jl:67-69)
-                const unsigned tz = ((unsigned)(__double2hiint(cc) | __double2hiint(dd) | __double2hiint(b)) << 1) |
-                                    (unsigned)(__double2loint(cc) | __double2loint(dd) | __double2loint(b));
+                const unsigned tz = ((unsigned)(__double2hiint(cc) | __double2hiint(b)) << 1) |
+                                    (unsigned)(__double2loint(cc) | __double2loint(b));
                 ok = q_exp_in(q, 1023u - 900u, 1023u + 900u) && (tz != 0u);
                 double yr0;
                 asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(yr0) : "d"(q));
@@ -740,12 +762,13 @@ template <class T, int CPL> struct FastSolver {
                 betan = -copysign(nrm, a);
                 const double rb = -copysign(yr, a);        // 1/beta
                 t1n = mk_cx<R>((betan - a) * rb, -b * rb);
+                tau2n = -cc * rb;                          // Re(tau v2) = -x2 / beta for a real tail x2
                 const double amb = a - betan;              // |amb| >= |beta|: no cancellation
                 const double den = fma(amb, amb, b * b);
                 const double e2 = fma(-den, y0, 1.0);
                 const double rm = fma(y0, fma(e2, e2, e2), y0);   // y0 (1 + e + e^2)
                 const double tr = amb * rm, ti = -b * rm;
-                v2n = mk_cx<R>(cc * tr - dd * ti, cc * ti + dd * tr);
+                v2n = mk_cx<R>(cc * tr, cc * ti);
             }
             // ---- bulk items: reflector k on the owned columns (left) / rows (right, conjugated) ----
 #pragma unroll
@@ -763,18 +786,19 @@ template <class T, int CPL> struct FastSolver {
             if (last) {
                 f_sub = n_v0;
                 f_diag = n_d00;
-                f_sup = f01;
                 break;
             }
             if (!ok) {
                 v0 = n_v0;
-                v1 = n_v1;
+                v1 = mk_cx<R>(n_v1, zero);
                 t1n = reflector_cplx2_generic<R>(v0, v1);
                 betan = v0.re;
                 v2n = v1;
+                tau2n = t1n.re * v2n.re - t1n.im * v2n.im;
             }
             tau1 = t1n;
             v2 = v2n;
+            tau2 = tau2n;
             beta = betan;
             d00 = n_d00;
             d10 = n_d10;
@@ -804,12 +828,11 @@ template <class T, int CPL> struct FastSolver {
             C v = c[s];
             if (fix) v = v * tphc;
             if (j >= iend + 1 && j <= n) HH(iend, j) = v;
-            if (j <= iend - 2) HH(j, iend) = cconj(v);
+            if (j <= iend - 1) HH(j, iend) = cconj(v);   // includes H[iend-1, iend], carried by the owner of row iend-1
         }
         if (lane == 0) {
             HH(iend, iend - 1) = mk_cx<R>(fsr, zero);
             HH(iend, iend) = f_diag;
-            HH(iend - 1, iend) = fix ? f_sup * tph : f_sup;
         }
         __syncwarp();
     }
@@ -1139,6 +1162,7 @@ template <class T, int CPL> struct FastSolver {
         R b01 = HH(mx, mx + 1), b11 = HH(mx + 1, mx + 1), b21 = HH(mx + 2, mx + 1);
         R tau1 = reflector_real_small(v0, v1, v2, 3);
         R beta = v0;
+        R tau2 = tau1 * v1, tau3 = tau1 * v2;
         R L10 = zero, L20 = zero, L11 = zero, L21 = zero, L12 = zero, L22 = zero, L01 = zero, L02 = zero;
         const int capz = wantZ ? cap : 0x7fffffff;
         const uint32_t ring32 = smem_u32(ring);
@@ -1174,7 +1198,6 @@ template <class T, int CPL> struct FastSolver {
                 lds_f64_if(c2[s], ak1 + ib[s], j == k - 1);
                 y[s] = lds_e<T>(ya);
             }
-            const R tau2 = tau1 * v1, tau3 = tau1 * v2;
             // ---- chain: rows k..k+2 of columns k..k+2 (left), then columns k..k+2 of rows k..k+3 (right) ----
             const R s0 = fma(v2, b20, fma(v1, b10, b00));
             const R a00 = fma(-s0, tau1, b00), a10 = fma(-s0, tau2, b10), a20 = fma(-s0, tau3, b20);
@@ -1210,27 +1233,30 @@ template <class T, int CPL> struct FastSolver {
             }
             cnt += 1;
             // ---- reflector k+1 from (f10, f20, f30), straight-line (general routine only for out-of-range input) ----
-            R t1n, v1n, v2n, betan;
+            R t1n, v1n, v2n, betan, tau2n, tau3n;
             bool ok;
             {
                 const double q = fma(f10, f10, fma(f20, f20, f30 * f30));
                 const unsigned tz = ((unsigned)(__double2hiint(f20) | __double2hiint(f30)) << 1) |
                                     (unsigned)(__double2loint(f20) | __double2loint(f30));
                 ok = q_exp_in(q, 1023u - 900u, 1023u + 900u) && (tz != 0u);
-                double yr;
-                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(yr) : "d"(q));
-                const double qy = q * yr;
-                const double e = fma(-qy, yr, 1.0);
+                double yr0;
+                asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(yr0) : "d"(q));
+                // seed of 1/(alpha - beta) from the unrefined norm: the second MUFU overlaps the refinement of the first
+                double y0;
+                asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(f10 + copysign(q * yr0, f10)));
+                const double qy = q * yr0;
+                const double e = fma(-qy, yr0, 1.0);
                 const double cf = fma(e, 0.375, 0.5);
-                yr = fma(yr * e, cf, yr);                 // 1/sqrt(q)
-                const double sq = q * yr;
-                const double rr = fma(-sq, sq, q);
-                const double nrm = fma(0.5 * yr, rr, sq);  // sqrt(q)
-                betan = -copysign(nrm, f10);
-                double rb = -copysign(yr, f10);            // ~ 1/beta
-                rb = fma(rb, fma(-betan, rb, 1.0), rb);
+                const double yr = fma(yr0 * e, cf, yr0);   // 1/sqrt(q), one cubic step
+                betan = -copysign(q * yr, f10);
+                const double rb = -copysign(yr, f10);      // 1/beta
                 t1n = (betan - f10) * rb;
-                const double tt = fast_rcp(f10 - betan);
+                tau2n = -f20 * rb;                         // tau v1 = -x1 / beta,  tau v2 = -x2 / beta
+                tau3n = -f30 * rb;
+                const double amb = f10 - betan;            // |amb| >= |beta|: no cancellation
+                const double e2 = fma(-amb, y0, 1.0);
+                const double tt = fma(y0, fma(e2, e2, e2), y0);
                 v1n = f20 * tt;
                 v2n = f30 * tt;
             }
@@ -1255,10 +1281,14 @@ template <class T, int CPL> struct FastSolver {
                 betan = w0;
                 v1n = w1;
                 v2n = w2;
+                tau2n = t1n * v1n;
+                tau3n = t1n * v2n;
             }
             tau1 = t1n;
             v1 = v1n;
             v2 = v2n;
+            tau2 = tau2n;
+            tau3 = tau3n;
             beta = betan;
             b00 = f11;
             b10 = f21;
