@@ -269,7 +269,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (development only)")
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the informational runs of the other BASELINE configs")
     args = ap.parse_args()
@@ -414,9 +414,10 @@ def main():
         alg_flops = (qr_flops if have_stage else flops_per_matrix) * batch
         alg_bytes = 3 * n * n * esz * batch + n * 16 * batch
         achieved_tf = alg_flops / (kernel_ms * 1e-3) / 1e12
-        # DRAM traffic of the same kernel from the committed ncu capture (profiles/r01_stageB_cfg3.summary.txt):
-        # 643 MB for a 2960-matrix launch = 217 KB per 64x64 c64 matrix (H, Q in; T, Z out), scaled to this launch
-        ncu_traffic_per_matrix = 217.3e3 if (kind == 1 and n == 64) else None
+        # DRAM traffic of the same kernel from the committed ncu capture (profiles/r01d_stageB_cfg3.summary.txt):
+        # 309 MB read + 826 MB written for a 2960-matrix launch = 383 KB per 64x64 c64 matrix (algorithmic: H, Q in and
+        # T, Z out = 262 KB; Z is streamed in place through L2 and dirty lines are written back more than once)
+        ncu_traffic_per_matrix = 383.5e3 if (kind == 1 and n == 64) else None
         roofline = {
             "bound": "fp64_fma", "kernel": "gschur_qr_kernel<cx<double>,2> (stage B: QR sweeps + Z)" if kind == 1 else "gschur_qr_kernel (stage B)",
             "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
@@ -429,7 +430,7 @@ def main():
             "whole_step": {"achieved": flops_per_matrix * batch / (step_mean * 1e-3) / 1e12,
                            "frac": flops_per_matrix * batch / (step_mean * 1e-3) / 1e12 / fp64_peak,
                            "algorithmic_flops_per_matrix": flops_per_matrix},
-            "stage_a": {"kernel": "gehrd_q_kernel (scale + Hessenberg + Q)", "kernel_ms": float(ms_a.value) if have_stage else None,
+            "stage_a": {"kernel": "gehrd_q_split_kernel (ComplexF64) / gehrd_q_kernel (scale + Hessenberg + Q)", "kernel_ms": float(ms_a.value) if have_stage else None,
                         "achieved": (hq_flops * batch / (ms_a.value * 1e-3) / 1e12) if have_stage and ms_a.value > 0 else None,
                         "algorithmic_flops_per_matrix": hq_flops},
             "hbm_view": {"achieved": alg_bytes / (step_mean * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",

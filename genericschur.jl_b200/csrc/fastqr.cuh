@@ -1206,11 +1206,36 @@ template <class T, int CPL> struct FastSolver {
             const R s2 = fma(v2, b22, fma(v1, b12, b02));
             const R a02 = fma(-s2, tau1, b02), a12 = fma(-s2, tau2, b12), a22 = fma(-s2, tau3, b22);
             const R t1 = fma(v2, a12, fma(v1, a11, a10));
-            const R f10 = fma(-t1, tau1, a10), f11 = fma(-t1, tau2, a11), f12 = fma(-t1, tau3, a12);   // row k+1
             const R t2 = fma(v2, a22, fma(v1, a21, a20));
-            const R f20 = fma(-t2, tau1, a20), f21 = fma(-t2, tau2, a21), f22 = fma(-t2, tau3, a22);   // row k+2
             const R t3 = v2 * e3;
-            const R f30 = -t3 * tau1, f31 = -t3 * tau2, f32 = fma(-t3, tau3, e3);                      // row k+3
+            // f10, f20, f30 = H[k+1..k+3, k] feed the next reflector: the serial chain.  tau1, tau2 = tau1 v1, tau3 = tau1 v2 come
+            // early out of the previous reflector (from 1/beta), v1 and v2 last (from 1/(alpha - beta)); the expressions
+            // are regrouped so that v enters once: with r_i = (1 - tau1) b_i0 - tau2 b_i1 - tau3 b_i2 (row i of the block
+            // times the right reflector's first column) and sx = r_0 + v1 r_1 + v2 r_2:
+            //   f10 = r_1 - tau2 sx,   f20 = r_2 - tau3 sx,   f30 = -tau3 e3.
+            // Measured on B200: the Float64 kernels run 8-12 CTAs per SM and are closer to issue-bound than chain-bound — the
+            // ten extra FMAs cost more than the shorter chain gains (32x32: +4 %, 64x64: +9 % stage-B time), so this is OFF.
+#ifndef GS_QR_REGROUP_REAL_MAXCPL
+#define GS_QR_REGROUP_REAL_MAXCPL 0
+#endif
+            R f10, f20, f30;
+            if constexpr (CPL <= GS_QR_REGROUP_REAL_MAXCPL) {
+                const R omt = one - tau1;
+                const R r0 = fma(-tau3, b02, fma(-tau2, b01, omt * b00));
+                const R r1 = fma(-tau3, b12, fma(-tau2, b11, omt * b10));
+                const R r2 = fma(-tau3, b22, fma(-tau2, b21, omt * b20));
+                const R sx = fma(v2, r2, fma(v1, r1, r0));
+                f10 = fma(-tau2, sx, r1);
+                f20 = fma(-tau3, sx, r2);
+                f30 = -(tau3 * e3);
+            } else {
+                f10 = fma(-t1, tau1, a10);
+                f20 = fma(-t2, tau1, a20);
+                f30 = -t3 * tau1;
+            }
+            const R f11 = fma(-t1, tau2, a11), f12 = fma(-t1, tau3, a12);   // row k+1
+            const R f21 = fma(-t2, tau2, a21), f22 = fma(-t2, tau3, a22);   // row k+2
+            const R f31 = -t3 * tau2, f32 = fma(-t3, tau3, e3);             // row k+3
             const R t0 = fma(v2, a02, fma(v1, a01, a00));
             const R f00 = fma(-t0, tau1, a00), f01 = fma(-t0, tau2, a01), f02 = fma(-t0, tau3, a02);   // row k: final
             const bool last = (k == iend - 2);
