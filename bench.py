@@ -147,7 +147,7 @@ def other_workloads(gs, torch, skip):
     out = {}
     stream = torch.cuda.current_stream().cuda_stream
 
-    def timed(fn, reps=2):
+    def timed(fn, reps=3):
         best = None
         for _ in range(reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -178,6 +178,21 @@ def other_workloads(gs, torch, skip):
                      "nominal_tflops": flops * batch / (ms * 1e-3) / 1e12, "unconverged": int((info != 0).sum().item())}
         del A0, A, Z, w, info
         torch.cuda.empty_cache()
+    # eigvals! path (wantZ = false — stage A skips Q, stage B runs without the Z-warp's work)
+    n, batch = 64, 16384
+    A0 = torch.rand((batch, n, n), dtype=torch.complex128, device="cuda")
+    A = torch.empty_like(A0)
+    w = torch.empty((batch, n), dtype=torch.complex128, device="cuda")
+    info = torch.zeros(batch, dtype=torch.int32, device="cuda")
+
+    def fnev():
+        A.copy_(A0)
+        gs.gschur_device_(1, n, batch, A.data_ptr(), None, w.data_ptr(), info.data_ptr(), stream=stream)
+    ms = timed(fnev) - timed(lambda: A.copy_(A0))
+    out["eigvals_c64n64"] = {"workload": "16384 x 64x64 ComplexF64, eigenvalues only (wantZ = false)",
+                             "matrices_per_s": batch / (ms * 1e-3), "ms": ms, "unconverged": int((info != 0).sum().item())}
+    del A0, A, w, info
+    torch.cuda.empty_cache()
     # cfg5: complex double-double, limbs (re.hi, re.lo, im.hi, im.lo) innermost
     n, batch = 96, 4096
     hi = torch.rand((batch, n, n, 2), dtype=torch.float64, device="cuda")

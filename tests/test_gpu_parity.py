@@ -105,6 +105,29 @@ def test_ragged_sizes(gs, O, kind, n, batch):
         _check_one(O, A[:, :, b], S.T[:, :, b], S.Z[:, :, b], S.values[:, b], kind, 10, f"n{n}b{b}")
 
 
+@pytest.mark.parametrize("kind,n", [(0, 7), (0, 32), (0, 50), (0, 64), (1, 7), (1, 32), (1, 50), (1, 64)])
+def test_stage_a_kernels_both_pass(gs, O, monkeypatch, kind, n):
+    """The two stage-A kernels (thread-per-column `gehrd_q_kernel` and split-column `gehrd_q_split_kernel`,
+    selected per kind by default, forced here with GSCHUR_GEHRD=v1|v2) reduce the same matrices: both decompositions
+    meet the reference's acceptance ratios and their eigenvalues agree (no bit-exactness: the reflector arithmetic of
+    the split kernel uses the guarded fast reciprocal / square root)."""
+    rng = np.random.default_rng(31 * n + kind)
+    batch = 5
+    A = np.asfortranarray(rng.random((n, n, batch)) + (1j * rng.random((n, n, batch)) if kind else 0))
+    out = {}
+    for which in ("v1", "v2"):
+        monkeypatch.setenv("GSCHUR_GEHRD", which)
+        S = gs.gschur(A)
+        assert not np.any(S.info)
+        for b in range(batch):
+            _check_one(O, A[:, :, b], S.T[:, :, b], S.Z[:, :, b], S.values[:, b], kind, 10, f"{which}n{n}b{b}")
+        out[which] = S
+    monkeypatch.delenv("GSCHUR_GEHRD")
+    for b in range(batch):
+        d = match_eigs(out["v1"].values[:, b], out["v2"].values[:, b])
+        assert np.max(d) <= 1e-11 * n * np.abs(A[:, :, b]).max(), (kind, n, b, float(np.max(d)))
+
+
 def test_empty_inputs(gs):
     S = gs.gschur(np.zeros((0, 0), order="F"))
     assert S.T.shape == (0, 0) and S.values.shape == (0,)
