@@ -4,6 +4,7 @@
 //    thread per device, no collective), each slice is pipelined in chunks over three streams so that
 //    H2D, compute and D2H overlap.
 // There is no CPU fallback anywhere in this file.
+#include <cstdlib>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -163,7 +164,8 @@ struct ChunkBuf {
     void *dA = nullptr, *dZ = nullptr, *dw = nullptr, *dtau = nullptr;
     int32_t* dinfo = nullptr;
     uint32_t* dstats = nullptr;
-    cudaStream_t stream = nullptr;
+    cudaEvent_t evH2D = nullptr, evComp = nullptr, evD2H = nullptr;   // this buffer's chunk: input landed / kernels done / results out
+    bool busy = false;                                                 // evD2H has been recorded in this call
     size_t capA = 0, capZ = 0, capw = 0, captau = 0, capn = 0, capst = 0;
 };
 
@@ -172,6 +174,11 @@ struct ChunkBuf {
 constexpr int NBUF = 4;
 struct DevicePipe {
     ChunkBuf buf[NBUF];
+    // Three streams: copies in, kernels, copies out.  The kernels of successive chunks are SERIALISED on one stream:
+    // both stages are persistent grids sized to fill the GPU, and letting the grids of two chunks compete for SMs made
+    // the end-to-end time bimodal (measured: 410 ms or 1000 ms for the same call, depending on which grid's CTAs became
+    // resident first).  Copies overlap the kernels through per-buffer events.
+    cudaStream_t sH2D = nullptr, sComp = nullptr, sD2H = nullptr;
     // pinned staging for the small outputs (w, info, stats, tau) of a whole slice: a D2H copy into the caller's
     // pageable arrays would block the enqueue loop until the chunk's kernels finish and serialise the pipeline
     char* hstage = nullptr;
@@ -206,7 +213,12 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
     const size_t mat = (size_t)n * n * es;
     const int64_t count = b1 - b0;
     // chunk size: aim at >= 16 chunks per slice but at least enough matrices to fill the GPU a few times over
-    int64_t chunk = (count + 15) / 16;
+    int nchunks = 8;
+    if (const char* e = std::getenv("GSCHUR_PIPE_CHUNKS")) {   // tuning knob
+        const int v = std::atoi(e);
+        if (v >= 1 && v <= 4096) nchunks = v;
+    }
+    int64_t chunk = (count + nchunks - 1) / nchunks;
     const int64_t min_chunk = 2048;
     if (chunk < min_chunk) chunk = min_chunk;
     if (chunk > count) chunk = count;
@@ -246,8 +258,14 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
         P.hcap = stage_bytes;
     }
     char* hst = P.hstage;
+    if (!P.sH2D) SL_TRY(cudaStreamCreateWithFlags(&P.sH2D, cudaStreamNonBlocking));
+    if (!P.sComp) SL_TRY(cudaStreamCreateWithFlags(&P.sComp, cudaStreamNonBlocking));
+    if (!P.sD2H) SL_TRY(cudaStreamCreateWithFlags(&P.sD2H, cudaStreamNonBlocking));
     for (int i = 0; i < NBUF; ++i) {
-        if (!buf[i].stream) SL_TRY(cudaStreamCreateWithFlags(&buf[i].stream, cudaStreamNonBlocking));
+        if (!buf[i].evH2D) SL_TRY(cudaEventCreateWithFlags(&buf[i].evH2D, cudaEventDisableTiming));
+        if (!buf[i].evComp) SL_TRY(cudaEventCreateWithFlags(&buf[i].evComp, cudaEventDisableTiming));
+        if (!buf[i].evD2H) SL_TRY(cudaEventCreateWithFlags(&buf[i].evD2H, cudaEventDisableTiming));
+        buf[i].busy = false;
         SL_TRY(grow(buf[i].dA, buf[i].capA, mat * chunk));
         if (wantZ) SL_TRY(grow(buf[i].dZ, buf[i].capZ, mat * chunk));
         if (!hess) SL_TRY(grow(buf[i].dw, buf[i].capw, ws * n * chunk));
@@ -256,12 +274,34 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
         SL_TRY(grow(buf[i].dstats, buf[i].capst, sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX * chunk));
     }
     {
-        int ci = 0;
-        for (int64_t c0 = b0; c0 < b1; c0 += chunk, ++ci) {
+        // Chunk schedule: full chunks in the middle, a quarter and a half chunk at either end — the first H2D and the last
+        // D2H are the only copies that nothing overlaps, so they are kept short (when the slice is large enough to matter).
+        std::vector<int64_t> sizes;
+        {
+            int64_t left = count;
+            const bool taper = count >= 4 * chunk && chunk >= 4 * min_chunk;
+            if (taper) {
+                sizes.push_back(chunk / 4);
+                sizes.push_back(chunk / 2);
+                left -= chunk / 4 + chunk / 2 + chunk / 2 + chunk / 4;
+            }
+            while (left > 0) {
+                const int64_t c = left < chunk ? left : chunk;
+                sizes.push_back(c);
+                left -= c;
+            }
+            if (taper) {
+                sizes.push_back(chunk / 2);
+                sizes.push_back(chunk / 4);
+            }
+        }
+        int64_t c0 = b0;
+        for (int ci = 0; ci < (int)sizes.size(); c0 += sizes[ci], ++ci) {
             ChunkBuf& B = buf[ci % NBUF];
-            const int64_t cn = (c0 + chunk <= b1) ? chunk : (b1 - c0);
-            cudaStream_t s = B.stream;
-            // H2D
+            const int64_t cn = sizes[ci];
+            cudaStream_t s = P.sH2D;
+            // H2D (after the previous chunk in this buffer has been copied out)
+            if (B.busy) SL_TRY(cudaStreamWaitEvent(P.sH2D, B.evD2H, 0));
             if (denseA) {
                 SL_TRY(cudaMemcpyAsync(B.dA, J.A + (size_t)c0 * J.strideA * es, mat * cn, cudaMemcpyHostToDevice, s));
             } else {
@@ -280,6 +320,9 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
                                                  (size_t)n * es, n, cudaMemcpyHostToDevice, s));
                 }
             }
+            SL_TRY(cudaEventRecord(B.evH2D, P.sH2D));
+            s = P.sComp;
+            SL_TRY(cudaStreamWaitEvent(P.sComp, B.evH2D, 0));
             int rc = enqueue_device(J.kind, J.mode, n, cn, B.dA, n, (int64_t)n * n, wantZ ? B.dZ : nullptr, n,
                                     (int64_t)n * n, B.dw, B.dtau, J.scale, J.maxiter, B.dinfo, B.dstats, s, J.flags);
             if (rc) {
@@ -288,6 +331,9 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
                 goto cleanup;
             }
             // D2H
+            SL_TRY(cudaEventRecord(B.evComp, P.sComp));
+            s = P.sD2H;
+            SL_TRY(cudaStreamWaitEvent(P.sD2H, B.evComp, 0));
             if (denseA) {
                 SL_TRY(cudaMemcpyAsync(J.A + (size_t)c0 * J.strideA * es, B.dA, mat * cn, cudaMemcpyDeviceToHost, s));
             } else {
@@ -317,11 +363,14 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
             if (J.stats && !hess)
                 SL_TRY(cudaMemcpyAsync(hst + off_stats + l0 * sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX, B.dstats,
                                        sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX * cn, cudaMemcpyDeviceToHost, s));
+            SL_TRY(cudaEventRecord(B.evD2H, P.sD2H));
+            B.busy = true;
         }
     }
 cleanup:
-    for (int i = 0; i < NBUF; ++i)
-        if (buf[i].stream) cudaStreamSynchronize(buf[i].stream);
+    if (P.sH2D) cudaStreamSynchronize(P.sH2D);
+    if (P.sComp) cudaStreamSynchronize(P.sComp);
+    if (P.sD2H) cudaStreamSynchronize(P.sD2H);
     if (rc_final == 0) {
         if (!hess) std::memcpy(J.w + (size_t)b0 * n * ws, hst + off_w, ws * n * (size_t)count);
         if (hess && n > 1) std::memcpy(J.tau + (size_t)b0 * tau_per, hst + off_w, tau_per * (size_t)count);
