@@ -33,6 +33,9 @@
 #ifndef GS_QR_MINB_F64_2
 #define GS_QR_MINB_F64_2 8   // 64x64 Float64
 #endif
+#ifndef GS_QR_MINB_C64_1
+#define GS_QR_MINB_C64_1 8   // n <= 32 ComplexF64: 128 registers, 8 CTAs per SM (measured: 6 -> 8 CTAs = -12 % stage-B time, 10 = spills)
+#endif
 #ifndef GS_ZRUN
 #define GS_ZRUN 8
 #endif
@@ -1760,6 +1763,7 @@ template <class T, int CPL> struct qr_min_blocks {
     static constexpr int value = (!etraits<T>::is_complex && CPL == 1 && sizeof(T) == 8) ? GS_QR_MINB_F64_1
                                  : (!etraits<T>::is_complex && CPL == 2 && sizeof(T) == 8) ? GS_QR_MINB_F64_2
                                  : (etraits<T>::is_complex && sizeof(T) == 16 && CPL == 2) ? 6   // 64x64 ComplexF64: six CTAs/SM fit in shared memory
+                                 : (etraits<T>::is_complex && sizeof(T) == 16 && CPL == 1) ? GS_QR_MINB_C64_1   // n <= 32: register-bound
                                  : 1;
 };
 
