@@ -4,6 +4,8 @@
 //    thread per device, no collective), each slice is pipelined in chunks over three streams so that
 //    H2D, compute and D2H overlap.
 // There is no CPU fallback anywhere in this file.
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <atomic>
 #include <cstdio>
@@ -208,6 +210,11 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
         }                                                                             \
     } while (0)
     int rc_final = 0;
+    // GSCHUR_PIPE_TRACE=1: one line per slice on stderr with host and device times of the pipeline (development aid)
+    const bool trace = std::getenv("GSCHUR_PIPE_TRACE") != nullptr;
+    cudaEvent_t tevK0 = nullptr, tevK1 = nullptr, tevD1 = nullptr;
+    double t_begin = 0, t_enq = 0;
+    auto now_s = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     const int n = J.n;
     const size_t es = elem_size(J.kind), ws = eig_size(J.kind);
     const size_t mat = (size_t)n * n * es;
@@ -296,6 +303,12 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
             }
         }
         int64_t c0 = b0;
+        if (trace) {
+            cudaEventCreate(&tevK0);
+            cudaEventCreate(&tevK1);
+            cudaEventCreate(&tevD1);
+            t_begin = now_s();
+        }
         for (int ci = 0; ci < (int)sizes.size(); c0 += sizes[ci], ++ci) {
             ChunkBuf& B = buf[ci % NBUF];
             const int64_t cn = sizes[ci];
@@ -323,6 +336,7 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
             SL_TRY(cudaEventRecord(B.evH2D, P.sH2D));
             s = P.sComp;
             SL_TRY(cudaStreamWaitEvent(P.sComp, B.evH2D, 0));
+            if (trace && ci == 0) cudaEventRecord(tevK0, P.sComp);
             int rc = enqueue_device(J.kind, J.mode, n, cn, B.dA, n, (int64_t)n * n, wantZ ? B.dZ : nullptr, n,
                                     (int64_t)n * n, B.dw, B.dtau, J.scale, J.maxiter, B.dinfo, B.dstats, s, J.flags);
             if (rc) {
@@ -366,11 +380,27 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
             SL_TRY(cudaEventRecord(B.evD2H, P.sD2H));
             B.busy = true;
         }
+        if (trace) {
+            cudaEventRecord(tevK1, P.sComp);
+            cudaEventRecord(tevD1, P.sD2H);
+            t_enq = now_s();
+        }
     }
 cleanup:
     if (P.sH2D) cudaStreamSynchronize(P.sH2D);
     if (P.sComp) cudaStreamSynchronize(P.sComp);
     if (P.sD2H) cudaStreamSynchronize(P.sD2H);
+    if (trace && tevK0) {
+        const double t_sync = now_s();
+        float k_ms = 0, d_ms = 0;
+        cudaEventElapsedTime(&k_ms, tevK0, tevK1);
+        cudaEventElapsedTime(&d_ms, tevK0, tevD1);
+        std::fprintf(stderr, "[gschur pipe] dev %d: enqueue %.1f ms, until sync %.1f ms; first kernel -> last kernel %.1f ms, -> last D2H %.1f ms\n",
+                     dev, 1e3 * (t_enq - t_begin), 1e3 * (t_sync - t_begin), k_ms, d_ms);
+        cudaEventDestroy(tevK0);
+        cudaEventDestroy(tevK1);
+        cudaEventDestroy(tevD1);
+    }
     if (rc_final == 0) {
         if (!hess) std::memcpy(J.w + (size_t)b0 * n * ws, hst + off_w, ws * n * (size_t)count);
         if (hess && n > 1) std::memcpy(J.tau + (size_t)b0 * tau_per, hst + off_w, tau_per * (size_t)count);

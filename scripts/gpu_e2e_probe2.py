@@ -18,7 +18,7 @@ for name, fn in (("H2D 4.3GB", lambda: d.copy_(Ah, non_blocking=True)), ("D2H 4.
 del d
 torch.cuda.empty_cache()
 Ah_np = Ah.numpy().T; Zh_np = Zh.numpy().T
-for it in range(5):
+for it in range(int(os.environ.get("E2E_CALLS", "5"))):
     Ah.copy_(A0c)
     t0 = time.perf_counter()
     S = gs.gschur_(Ah_np, Z=Zh_np, devices=[0])
