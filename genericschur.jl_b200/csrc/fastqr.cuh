@@ -55,28 +55,57 @@ template <class R> struct __align__(16) zop_t<false, R> {   // Float64: 32 B
 };
 
 struct zring_hdr {
-    int count[2];
-    int end[2];
+    int count[4];
+    int end[4];
 };
 
-// named barriers with immediate ids (a register id would make ptxas reserve all 16 barriers per CTA)
-enum { BAR_FULL0 = 1, BAR_EMPTY0 = 3 };
+// Number of buffers of the reflector ring between the H-warp and the Z-warp.  ComplexF64 uses three (the H-warp may run
+// two buffers = 32 bulge steps ahead): with two, the SASS-level profile showed the H-warp waiting ~900 cycles per buffer
+// hand-over for the Z-warp's slow buffers (Z columns that had left L2).  The other kinds keep two: their kernels run up
+// to 12 CTAs per SM and the SM has barrier slots for 12 x 5 named barriers, not 12 x 7.
+template <class T> struct ring_bufs { static constexpr int value = 2; };
+template <> struct ring_bufs<cx<double>> { static constexpr int value = 3; };
+
+// named barriers with immediate ids (a register id would make ptxas reserve all 16 barriers per CTA):
+// full[b] = 1 + b, empty[b] = 1 + RB + b
 template <int ID> GS_DEV void bar_sync_imm() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
 template <int ID> GS_DEV void bar_arrive_imm() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
-GS_DEV void named_bar_sync(int id, int) {
-    switch (id) {
-        case 1: bar_sync_imm<1>(); break;
-        case 2: bar_sync_imm<2>(); break;
-        case 3: bar_sync_imm<3>(); break;
-        default: bar_sync_imm<4>(); break;
+template <int RB> GS_DEV void named_bar_sync(int id) {
+    if constexpr (RB == 2) {
+        switch (id) {
+            case 1: bar_sync_imm<1>(); break;
+            case 2: bar_sync_imm<2>(); break;
+            case 3: bar_sync_imm<3>(); break;
+            default: bar_sync_imm<4>(); break;
+        }
+    } else {
+        switch (id) {
+            case 1: bar_sync_imm<1>(); break;
+            case 2: bar_sync_imm<2>(); break;
+            case 3: bar_sync_imm<3>(); break;
+            case 4: bar_sync_imm<4>(); break;
+            case 5: bar_sync_imm<5>(); break;
+            default: bar_sync_imm<6>(); break;
+        }
     }
 }
-GS_DEV void named_bar_arrive(int id, int) {
-    switch (id) {
-        case 1: bar_arrive_imm<1>(); break;
-        case 2: bar_arrive_imm<2>(); break;
-        case 3: bar_arrive_imm<3>(); break;
-        default: bar_arrive_imm<4>(); break;
+template <int RB> GS_DEV void named_bar_arrive(int id) {
+    if constexpr (RB == 2) {
+        switch (id) {
+            case 1: bar_arrive_imm<1>(); break;
+            case 2: bar_arrive_imm<2>(); break;
+            case 3: bar_arrive_imm<3>(); break;
+            default: bar_arrive_imm<4>(); break;
+        }
+    } else {
+        switch (id) {
+            case 1: bar_arrive_imm<1>(); break;
+            case 2: bar_arrive_imm<2>(); break;
+            case 3: bar_arrive_imm<3>(); break;
+            case 4: bar_arrive_imm<4>(); break;
+            case 5: bar_arrive_imm<5>(); break;
+            default: bar_arrive_imm<6>(); break;
+        }
     }
 }
 
@@ -150,6 +179,9 @@ template <class T, int CPL> struct FastSolver {
     typedef zop_t<CPLX, R> ZOp;
 
     static constexpr int EX = CPLX ? 2 : 3;   // rows stored below the diagonal in each packed column
+    static constexpr int RB = ring_bufs<T>::value;       // ring buffers (2 or 3)
+    static constexpr int BAR_FULL0 = 1, BAR_EMPTY0 = 1 + RB;
+    int rbase;                                           // first record of the buffer being filled: (sidx % RB) * cap
     int n, ldz, lane, cap;
     T* H;            // packed upper Hessenberg (+ bulge slots), shared memory
     T* Z;            // Schur vectors, global memory (column-major, leading dimension ldz)
@@ -228,11 +260,12 @@ template <class T, int CPL> struct FastSolver {
     // producer side of the Z ring
     // ------------------------------------------------------------------------------------------------
     GS_DEV void begin_buffer() {
+        rbase = (sidx % RB) * cap;
         if (!wantZ) return;
 #ifdef GS_QR_PROFILE
         const long long tb0 = clock64();
 #endif
-        if (sidx >= 2) named_bar_sync(BAR_EMPTY0 + (sidx & 1), 64);
+        if (sidx >= RB) named_bar_sync<RB>(BAR_EMPTY0 + sidx % RB);
 #ifdef GS_QR_PROFILE
         prof[1] += clock64() - tb0;
 #endif
@@ -240,13 +273,13 @@ template <class T, int CPL> struct FastSolver {
     }
     GS_DEV void publish(int end) {
         if (!wantZ) return;
-        const int b = sidx & 1;
+        const int b = sidx % RB;
         if (lane == 0) {
             hdr->count[b] = cnt;
             hdr->end[b] = end;
         }
         __syncwarp();
-        named_bar_arrive(BAR_FULL0 + b, 64);
+        named_bar_arrive<RB>(BAR_FULL0 + b);
         sidx += 1;
     }
     GS_DEV void ensure_space(int m) {
@@ -256,7 +289,7 @@ template <class T, int CPL> struct FastSolver {
             begin_buffer();
         }
     }
-    GS_DEV ZOp* slot() { return ring + (sidx & 1) * cap + cnt; }
+    GS_DEV ZOp* slot() { return ring + rbase + cnt; }
     // make room for m ops once, so that the step loop can push without checking
     GS_DEV void reserve_ops(int) {}   // (the ring is small: every push checks for space, see push_*)
     GS_DEV void push_refl_c(int k, const C& tau1, const C& v2) {
@@ -266,7 +299,7 @@ template <class T, int CPL> struct FastSolver {
             begin_buffer();
         }
         if (lane == 0) {
-            ZOp* e = ring + (sidx & 1) * cap + cnt;
+            ZOp* e = ring + rbase + cnt;
             if constexpr (CPLX) {
                 e->op = ZOP_REFL;
                 e->k = k;
@@ -285,7 +318,7 @@ template <class T, int CPL> struct FastSolver {
             begin_buffer();
         }
         if (lane == 0) {
-            ZOp* e = ring + (sidx & 1) * cap + cnt;
+            ZOp* e = ring + rbase + cnt;
             if constexpr (!CPLX) {
                 e->op = op;
                 e->k = k;
@@ -299,9 +332,9 @@ template <class T, int CPL> struct FastSolver {
     GS_DEV void finish_ring() {
         if (!wantZ) return;
         publish(1);
-        // balance the outstanding "empty" arrivals of the last two buffers
+        // balance the outstanding "empty" arrivals of the last RB buffers
         const int last = sidx - 1;
-        for (int c = (last - 1 < 0 ? 0 : last - 1); c <= last; ++c) named_bar_sync(BAR_EMPTY0 + (c & 1), 64);
+        for (int c = (last - (RB - 1) < 0 ? 0 : last - (RB - 1)); c <= last; ++c) named_bar_sync<RB>(BAR_EMPTY0 + c % RB);
     }
 
     // ================================================================================================
@@ -728,7 +761,7 @@ template <class T, int CPL> struct FastSolver {
             const bool last = (k == iend - 1);
             {
                 const bool l0 = lane == 0;
-                const uint32_t re = ring32 + (uint32_t)sizeof(ZOp) * (uint32_t)((sidx & 1) * cap + cnt);
+                const uint32_t re = ring32 + (uint32_t)sizeof(ZOp) * (uint32_t)(rbase + cnt);
                 sts_2i_if(re, (int)ZOP_REFL, k, l0 && wantZ);
                 sts_c64_if(re + 16, tau1, l0 && wantZ);
                 sts_c64_if(re + 32, v2, l0 && wantZ);
@@ -1244,7 +1277,7 @@ template <class T, int CPL> struct FastSolver {
             const bool last = (k == iend - 2);
             {
                 const bool l0 = lane == 0;
-                const uint32_t re = ring32 + (uint32_t)sizeof(ZOp) * (uint32_t)((sidx & 1) * cap + cnt);
+                const uint32_t re = ring32 + (uint32_t)sizeof(ZOp) * (uint32_t)(rbase + cnt);
                 sts_2i_if(re, (int)ZOP_REFL3, k, l0 && wantZ);
                 sts_f64_if(re + 8, tau1, l0 && wantZ);
                 sts_f64_if(re + 16, v1, l0 && wantZ);
@@ -1521,8 +1554,8 @@ template <class T, int CPL> struct FastSolver {
     GS_DEV void z_consumer() {
         const R zero = r_const<R>(0.0);
         for (int cidx = 0;; ++cidx) {
-            const int b = cidx & 1;
-            named_bar_sync(BAR_FULL0 + b, 64);
+            const int b = cidx % RB;
+            named_bar_sync<RB>(BAR_FULL0 + b);
             const int count = hdr->count[b];
             const int end = hdr->end[b];
             const ZOp* ops = ring + b * cap;
@@ -1711,7 +1744,7 @@ template <class T, int CPL> struct FastSolver {
                     }
                 }
             }
-            named_bar_arrive(BAR_EMPTY0 + b, 64);
+            named_bar_arrive<RB>(BAR_EMPTY0 + b);
             if (end) break;
         }
     }
@@ -1746,15 +1779,17 @@ template <class T, int CPL> struct fast_smem_layout {
     typedef smem_layout<T> L;
     typedef FastSolver<T, CPL> FS;
     typedef zop_t<etraits<T>::is_complex, typename etraits<T>::real> ZOp;
-    // A short ring (16 reflectors per buffer, two buffers): the H-warp publishes every 16 bulge steps.  Together with
-    // dropping the eigenvalue array for complex kinds (their eigenvalues are diag(T)) this brings a 64x64 ComplexF64
-    // matrix to 36.9 KB of shared memory: six CTAs per SM instead of five.
+    // A short ring (16 reflectors per buffer; two buffers, three for ComplexF64): the H-warp publishes every 16 bulge
+    // steps.  Together with dropping the eigenvalue array for complex kinds (their eigenvalues are diag(T)) a 64x64
+    // ComplexF64 matrix needs 37.6 KB of shared memory: six CTAs per SM (the limit is 37.8 KB).
     __host__ __device__ static int cap(int) { return 16; }
     __host__ __device__ static size_t off_w(int n) { return L::up16((size_t)FS::packed_elems(n) * sizeof(T)); }
     __host__ __device__ static size_t off_ring(int n) {
         return off_w(n) + (etraits<T>::is_complex ? 0 : L::up16((size_t)n * 2 * sizeof(R)));
     }
-    __host__ __device__ static size_t off_hdr(int n) { return off_ring(n) + L::up16(2 * (size_t)cap(n) * sizeof(ZOp)); }
+    __host__ __device__ static size_t off_hdr(int n) {
+        return off_ring(n) + L::up16((size_t)ring_bufs<T>::value * (size_t)cap(n) * sizeof(ZOp));
+    }
     __host__ __device__ static size_t bytes(int n) { return off_hdr(n) + L::up16(sizeof(zring_hdr)); }
 };
 
