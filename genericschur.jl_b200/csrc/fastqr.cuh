@@ -28,7 +28,7 @@
 #include "gehrd_split.cuh"
 
 #ifndef GS_QR_MINB_F64_1
-#define GS_QR_MINB_F64_1 12  // 32x32 Float64: CTAs per SM the register budget is sized for
+#define GS_QR_MINB_F64_1 9   // 32x32 Float64: CTAs per SM the register budget is sized for (9 x 7 named barriers fit an SM)
 #endif
 #ifndef GS_QR_MINB_F64_2
 #define GS_QR_MINB_F64_2 8   // 64x64 Float64
@@ -59,12 +59,21 @@ struct zring_hdr {
     int end[4];
 };
 
-// Number of buffers of the reflector ring between the H-warp and the Z-warp.  ComplexF64 uses three (the H-warp may run
-// two buffers = 32 bulge steps ahead): with two, the SASS-level profile showed the H-warp waiting ~900 cycles per buffer
-// hand-over for the Z-warp's slow buffers (Z columns that had left L2).  The other kinds keep two: their kernels run up
-// to 12 CTAs per SM and the SM has barrier slots for 12 x 5 named barriers, not 12 x 7.
-template <class T> struct ring_bufs { static constexpr int value = 2; };
-template <> struct ring_bufs<cx<double>> { static constexpr int value = 3; };
+// Number of buffers of the reflector ring between the H-warp and the Z-warp.  The Float64 / ComplexF64 kernels use
+// three (the H-warp may run two buffers = 32 bulge steps ahead): with two, the SASS-level profile showed the H-warp
+// waiting ~900 cycles per buffer hand-over for the Z-warp's slow buffers (Z columns that had left L2); measured gain of
+// the third buffer: 6 % of stage B at n = 64 (both kinds).  An SM has slots for 64 named barriers, i.e. 9 CTAs with
+// 7 barriers each; the double-double kinds keep two buffers.
+template <class T, int CPL> struct ring_bufs { static constexpr int value = 2; };
+template <int CPL> struct ring_bufs<cx<double>, CPL> { static constexpr int value = 3; };
+#ifndef GS_RING_F64_2
+#define GS_RING_F64_2 3   // 64x64 Float64 (8 CTAs per SM x 7 barriers fit)
+#endif
+template <> struct ring_bufs<double, 2> { static constexpr int value = GS_RING_F64_2; };
+#ifndef GS_RING_F64_1
+#define GS_RING_F64_1 3   // 32x32 Float64 at 9 CTAs per SM (measured: 12 CTAs x 2 buffers 6.72 ms, 9 x 3 buffers 6.60 ms per 16384)
+#endif
+template <> struct ring_bufs<double, 1> { static constexpr int value = GS_RING_F64_1; };
 
 // named barriers with immediate ids (a register id would make ptxas reserve all 16 barriers per CTA):
 // full[b] = 1 + b, empty[b] = 1 + RB + b
@@ -179,7 +188,7 @@ template <class T, int CPL> struct FastSolver {
     typedef zop_t<CPLX, R> ZOp;
 
     static constexpr int EX = CPLX ? 2 : 3;   // rows stored below the diagonal in each packed column
-    static constexpr int RB = ring_bufs<T>::value;       // ring buffers (2 or 3)
+    static constexpr int RB = ring_bufs<T, CPL>::value;  // ring buffers (2 or 3)
     static constexpr int BAR_FULL0 = 1, BAR_EMPTY0 = 1 + RB;
     int rbase;                                           // first record of the buffer being filled: (sidx % RB) * cap
     int n, ldz, lane, cap;
@@ -1788,7 +1797,7 @@ template <class T, int CPL> struct fast_smem_layout {
         return off_w(n) + (etraits<T>::is_complex ? 0 : L::up16((size_t)n * 2 * sizeof(R)));
     }
     __host__ __device__ static size_t off_hdr(int n) {
-        return off_ring(n) + L::up16((size_t)ring_bufs<T>::value * (size_t)cap(n) * sizeof(ZOp));
+        return off_ring(n) + L::up16((size_t)ring_bufs<T, CPL>::value * (size_t)cap(n) * sizeof(ZOp));
     }
     __host__ __device__ static size_t bytes(int n) { return off_hdr(n) + L::up16(sizeof(zring_hdr)); }
 };
