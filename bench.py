@@ -432,10 +432,10 @@ def main():
         alg_flops = (qr_flops if have_stage else flops_per_matrix) * batch
         alg_bytes = 3 * n * n * esz * batch + n * 16 * batch
         achieved_tf = alg_flops / (kernel_ms * 1e-3) / 1e12
-        # DRAM traffic of the same kernel from the committed ncu capture (profiles/r01d_stageB_cfg3.summary.txt):
-        # 309 MB read + 826 MB written for a 2960-matrix launch = 383 KB per 64x64 c64 matrix (algorithmic: H, Q in and
+        # DRAM traffic of the same kernel from the committed ncu capture (profiles/r01f_stageB_cfg3.summary.txt):
+        # 310 MB read + 753 MB written for a 2960-matrix launch = 359 KB per 64x64 c64 matrix (algorithmic: H, Q in and
         # T, Z out = 262 KB; Z is streamed in place through L2 and dirty lines are written back more than once)
-        ncu_traffic_per_matrix = 383.5e3 if (kind == 1 and n == 64) else None
+        ncu_traffic_per_matrix = 359.1e3 if (kind == 1 and n == 64) else None
         roofline = {
             "bound": "fp64_fma", "kernel": "gschur_qr_kernel<cx<double>,2> (stage B: QR sweeps + Z)" if kind == 1 else "gschur_qr_kernel (stage B)",
             "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
