@@ -174,6 +174,23 @@ def test_strided_and_split_invariance(gs):
     assert np.all(big[n:, :, :] == 0) and np.all(big[:, n:, :] == 0)
 
 
+def test_all_devices_in_process(gs, O):
+    """host-pointer mode with the batch split over every visible GPU from ONE process (one host thread
+    and one three-stream pipeline per device, no collective): bit-identical to the single-device result."""
+    ndev = gs.device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two GPUs")
+    rng = np.random.default_rng(77)
+    n, batch = 48, 4096 + 37
+    A = np.asfortranarray(rng.random((n, n, batch)) + 1j * rng.random((n, n, batch)))
+    S1 = gs.gschur(A, devices=[0])
+    S2 = gs.gschur(A, devices=list(range(ndev)))
+    assert not np.any(S2.info)
+    assert np.array_equal(S1.T, S2.T) and np.array_equal(S1.Z, S2.Z) and np.array_equal(S1.values, S2.values)
+    for b in (0, batch // 2, batch - 1):
+        _check_one(O, A[:, :, b], S2.T[:, :, b], S2.Z[:, :, b], S2.values[:, b], 1, 10, f"b{b}")
+
+
 def test_hessenberg(gs, O):
     """hesstest (test/complex.jl:36-61, test/real.jl:76-99) incl. the tiny / huge scalings; sub-diagonal real."""
     rng = np.random.default_rng(1234)
