@@ -9,16 +9,16 @@
 //     bulge step costs one shared-memory load and one store per owned column/row instead of 2-3 each, and the
 //     only synchronisation on the critical path is __syncwarp.  Lanes on the diagonal publish / refresh their
 //     carries through shared memory, which is also where the next reflector's vector is picked up.
-//   * the Z-warp (warp 1) applies the reflectors to the Schur vectors.  It receives them a sweep at a time through
-//     a double-buffered record in shared memory (named barriers full[2] / empty[2]) and streams them through
-//     carry registers as well (one load + one store per row and step).  It never blocks the H-warp unless it
-//     falls two sweeps behind.
+//   * the Z-warp (warp 1) applies the reflectors to the Schur vectors.  It receives them 16 at a time through a ring of
+//     record buffers in shared memory (named barriers full[b] / empty[b]; three buffers for Float64 / ComplexF64, two for
+//     the double-double kinds) and streams them through carry registers as well (one load + one store per row and step).
+//     It never blocks the H-warp unless it falls two buffers (32 bulge steps) behind.
 //
 // Storage.  The Hessenberg matrix is kept in PACKED form in shared memory — column j holds rows 1..j+EX, EX = 2
 // (complex: one bulge entry below the sub-diagonal) or 3 (real double shift: two) — which halves its footprint
 // (64x64 ComplexF64: 35 KB instead of 65 KB).  Z is NOT kept on chip: nothing on the critical path ever reads it, so
 // the Z-warp streams it through L2 (one coalesced column load and store per reflector, software-prefetched) in
-// place in the caller's Z buffer.  Together that is ~45 KB of shared memory per matrix instead of 142 KB, i.e. five
+// place in the caller's Z buffer.  Together that is 37.6 KB of shared memory per matrix instead of 142 KB, i.e. six
 // CTAs per SM instead of one — occupancy is what this latency-bound algorithm needs.
 //
 // The arithmetic per reflector application and every decision rule are those of batched.cuh (and of the
