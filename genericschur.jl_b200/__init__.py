@@ -122,6 +122,17 @@ def measure_fp64_peak():
     return t.value, ms.value
 
 
+def measure_l2_bandwidth():
+    """(GB/s read + written, ms) of an L2-resident read-modify-write stream on the current device: the ceiling of
+    stage B's Z stream."""
+    g = ctypes.c_double(0.0)
+    ms = ctypes.c_double(0.0)
+    rc = _lib.lib().gschur_cuda_measure_l2_bandwidth(ctypes.byref(g), ctypes.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"gschur_cuda_measure_l2_bandwidth failed: {rc}")
+    return g.value, ms.value
+
+
 def max_batched_n(kind):
     return _lib.lib().gschur_cuda_max_batched_n(kind)
 

@@ -27,6 +27,7 @@ EXPORTS = [
     "gschur_cuda_batched_async",
     "gschur_cuda_hessenberg_batched",
     "gschur_cuda_measure_fp64_peak",
+    "gschur_cuda_measure_l2_bandwidth",
     "gschur_cuda_stage_timing",
     "gschur_cuda_hessenberg_large",
     "gschur_cuda_large",
@@ -67,6 +68,8 @@ def lib():
         L.gschur_cuda_hessenberg_batched.restype = ci
         L.gschur_cuda_measure_fp64_peak.argtypes = [vp, vp]
         L.gschur_cuda_measure_fp64_peak.restype = ci
+        L.gschur_cuda_measure_l2_bandwidth.argtypes = [vp, vp]
+        L.gschur_cuda_measure_l2_bandwidth.restype = ci
         cd = ctypes.c_double
         L.gschur_cuda_hessenberg_large.argtypes = [ci, vp, ci, vp, vp, ci, u32]
         L.gschur_cuda_hessenberg_large.restype = ci

@@ -24,6 +24,28 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, 
     double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
     if (s == 123.456) out[0] = s;   // keeps the chains live without a store in the common case
 }
+
+// L2 streaming probe: every thread reads, touches and writes back its own 16-byte words of a buffer that fits in L2,
+// `passes` times, with the cache-global (L1-bypassing) accesses stage B's Z-warp uses.  Four independent words in
+// flight per thread; n4 is a multiple of 4 * gridDim.x * blockDim.x.
+__global__ void __launch_bounds__(256) l2_stream_kernel(uint4* buf, size_t n4, int passes) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int p = 0; p < passes; ++p) {
+        for (size_t i = i0; i < n4; i += 4 * stride) {
+            uint4 v0 = __ldcg(buf + i), v1 = __ldcg(buf + i + stride);
+            uint4 v2 = __ldcg(buf + i + 2 * stride), v3 = __ldcg(buf + i + 3 * stride);
+            v0.x += 1u;
+            v1.x += 1u;
+            v2.x += 1u;
+            v3.x += 1u;
+            __stcg(buf + i, v0);
+            __stcg(buf + i + stride, v1);
+            __stcg(buf + i + 2 * stride, v2);
+            __stcg(buf + i + 3 * stride, v3);
+        }
+    }
+}
 }  // namespace
 
 extern "C" int gschur_cuda_measure_fp64_peak(double* tflops, double* ms_out) {
@@ -55,6 +77,40 @@ extern "C" int gschur_cuda_measure_fp64_peak(double* tflops, double* ms_out) {
     cudaFree(d);
     double flops = 2.0 * 8.0 * 16.0 * (double)iters * (double)threads * (double)blocks;
     *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return 0;
+}
+
+extern "C" int gschur_cuda_measure_l2_bandwidth(double* gbs, double* ms_out) {
+    int dev = 0;
+    if (!gbs || cudaGetDevice(&dev) != cudaSuccess) return GSCHUR_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return GSCHUR_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, passes = 64;
+    const size_t n4 = (size_t)blocks * threads * 8;   // 148 SMs: 2.4 M words = 38.8 MB, well inside the 126 MB L2
+    uint4* d = nullptr;
+    if (cudaMalloc(&d, n4 * sizeof(uint4)) != cudaSuccess) return GSCHUR_ERR_CUDA;
+    cudaMemset(d, 0, n4 * sizeof(uint4));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {   // the first repetition also pulls the buffer into L2
+        cudaEventRecord(e0);
+        l2_stream_kernel<<<blocks, threads>>>(d, n4, passes);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) {
+            cudaFree(d);
+            return GSCHUR_ERR_CUDA;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    *gbs = 2.0 * (double)(n4 * sizeof(uint4)) * passes / (best * 1e-3) / 1e9;   // bytes read + bytes written
     if (ms_out) *ms_out = best;
     return 0;
 }

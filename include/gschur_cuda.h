@@ -101,6 +101,14 @@ int gschur_cuda_batched_async(int kind, int n, int64_t batch,
 int gschur_cuda_measure_fp64_peak(double* tflops, double* ms);
 
 /*
+ * Measures the L2 streaming bandwidth of the current device: a 38.8 MB buffer (resident in the 126 MB L2) is read
+ * and written back 64 times with L1-bypassing 16-byte accesses, the access pattern of stage B's Z stream (DESIGN.md
+ * section 6: the L2 ceiling behind the FP64 one).  *gbs receives (bytes read + bytes written) / s / 1e9, *ms (NULL
+ * ok) the best kernel time.
+ */
+int gschur_cuda_measure_l2_bandwidth(double* gbs, double* ms);
+
+/*
  * Per-kernel timing of the two-kernel batched path (stage A: scale + Hessenberg + Q; stage B: QR iteration), used by
  * bench.py for the per-kernel roofline.  enable: 1 / 0 switches CUDA-event recording on the launching stream on / off,
  * -1 leaves it unchanged; when both pointers are given the times (ms) of the most recent call are returned.
