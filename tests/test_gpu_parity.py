@@ -376,6 +376,15 @@ def test_larger_n_two_kernel_path(gs, O):
         gs.gschur(np.asfortranarray(rng.random((129, 129)) + 0j))      # no large-matrix path for ComplexF64
 
 
+def test_roofline_probes(gs):
+    """The two roofline denominators the library measures itself: DFMA peak and L2 streaming bandwidth (on a B200:
+    34.2 TFLOP/s and 12.9 TB/s, profiles/r01g_l2_probe.json).  Loose sanity bounds only."""
+    t, ms = gs.measure_fp64_peak()
+    assert 5.0 < t < 80.0 and ms > 0
+    g, ms = gs.measure_l2_bandwidth()
+    assert 2000.0 < g < 40000.0 and ms > 0
+
+
 def test_dmma_gemm(gs):
     """The library's FP64 tensor-core GEMM (mma.sync m8n8k4, SASS DMMA) against torch.matmul in float64."""
     import ctypes
