@@ -83,7 +83,8 @@ extern "C" int gschur_cuda_measure_fp64_peak(double* tflops, double* ms_out) {
 
 extern "C" int gschur_cuda_measure_l2_bandwidth(double* gbs, double* ms_out) {
     int dev = 0;
-    if (!gbs || cudaGetDevice(&dev) != cudaSuccess) return GSCHUR_ERR_CUDA;
+    if (!gbs) return GSCHUR_ERR_ARG;
+    if (cudaGetDevice(&dev) != cudaSuccess) return GSCHUR_ERR_CUDA;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return GSCHUR_ERR_CUDA;
     const int blocks = prop.multiProcessorCount * 8, threads = 256, passes = 64;
