@@ -455,6 +455,20 @@ def main():
                          "frac": alg_bytes / (step_mean * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                          "algorithmic_bytes_per_matrix": alg_bytes // batch},
         }
+        # L2 view of the same kernel: bytes it moves through L2 per matrix (lts__t_sectors x 32 B of the committed ncu
+        # captures: profiles/r01f_stageB_cfg3.ncu-rep 20.4 MB per 64x64 c64 matrix, r01b_stageB_f64n64.ncu-rep 6.0 MB per
+        # 64x64 f64 matrix — the Z stream) against the L2 streaming bandwidth measured live.
+        roofline["l2_view"] = None
+        l2_per_matrix = {(1, 64): 20.36e6, (0, 64): 6.01e6}.get((kind, n))
+        if l2_per_matrix:
+            try:
+                l2_peak, _ = gs.measure_l2_bandwidth()
+                l2_ach = l2_per_matrix * batch / (kernel_ms * 1e-3) / 1e9
+                roofline["l2_view"] = {"achieved": l2_ach, "peak": l2_peak, "unit": "GB/s", "frac": l2_ach / l2_peak,
+                                       "l2_bytes_per_matrix": l2_per_matrix,
+                                       "peak_source": "measured live (library L2 read-modify-write stream, 38.8 MB resident)"}
+            except Exception as exc:   # the probe is informational: never lose the bench line over it
+                roofline["l2_view"] = {"error": str(exc)}
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cpu, _, _ = cpu_baseline(kind, n, batch, 1234 + 3)
