@@ -29,6 +29,7 @@ EXPORTS = [
     "gschur_cuda_measure_fp64_peak",
     "gschur_cuda_measure_l2_bandwidth",
     "gschur_cuda_stage_timing",
+    "gschur_cuda_stage_timing3",
     "gschur_cuda_hessenberg_large",
     "gschur_cuda_large",
     "gschur_cuda_dgemm",
@@ -75,6 +76,8 @@ def lib():
         L.gschur_cuda_hessenberg_large.restype = ci
         L.gschur_cuda_stage_timing.argtypes = [ci, vp, vp]
         L.gschur_cuda_stage_timing.restype = ci
+        L.gschur_cuda_stage_timing3.argtypes = [ci, vp, vp, vp]
+        L.gschur_cuda_stage_timing3.restype = ci
         L.gschur_cuda_large.argtypes = [ci, vp, ci, vp, ci, vp, ci, vp, vp, u32]
         L.gschur_cuda_large.restype = ci
         L.gschur_cuda_dgemm.argtypes = [ci, ci, ci, ci, ci, cd, vp, ci, vp, ci, cd, vp, ci]

@@ -26,6 +26,7 @@
 #pragma once
 #include <cstdlib>
 #include "gehrd_split.cuh"
+#include "qrlog.cuh"
 
 #ifndef GS_QR_MINB_F64_1
 #define GS_QR_MINB_F64_1 9   // 32x32 Float64: CTAs per SM the register budget is sized for (9 x 7 named barriers fit an SM)
@@ -43,6 +44,7 @@
 namespace gs {
 
 enum { ZOP_REFL = 1, ZOP_SCALE = 2, ZOP_REFL3 = 3, ZOP_REFL2 = 4, ZOP_GIVENS = 5 };
+enum { LOG_OVERFLOW_RC = -100 };   // FastSolver<..., LOG>::qr_*: the matrix's reflector log is full
 
 template <bool CPLX, class R> struct zop_t;
 template <class R> struct __align__(16) zop_t<true, R> {    // 16 B + 4 reals
@@ -181,7 +183,9 @@ GS_DEV void lds_f64_if(double& v, uint32_t a, bool p) {
     asm volatile("{ .reg .pred q; setp.ne.b32 q, %2, 0; @q ld.shared.f64 %0, [%1]; }" : "+d"(v) : "r"(a), "r"((int)p));
 }
 
-template <class T, int CPL> struct FastSolver {
+// LOG = true: the three-stage path.  There is no Z-warp and no ring; every transformation applied from the right goes to
+// the global-memory log (qrlog.cuh) that stage C replays on Z.
+template <class T, int CPL, bool LOG = false> struct FastSolver {
     typedef typename etraits<T>::real R;
     typedef cx<R> C;
     static constexpr bool CPLX = etraits<T>::is_complex;
@@ -198,6 +202,7 @@ template <class T, int CPL> struct FastSolver {
     ZOp* ring;        // [2][cap]
     zring_hdr* hdr;
     bool wantZ;
+    LogWriter<R> lg;   // LOG only
     unsigned* stp;
     // producer state (uniform across the H-warp)
     int sidx, cnt;
@@ -269,6 +274,7 @@ template <class T, int CPL> struct FastSolver {
     // producer side of the Z ring
     // ------------------------------------------------------------------------------------------------
     GS_DEV void begin_buffer() {
+        if constexpr (LOG) return;
         rbase = (sidx % RB) * cap;
         if (!wantZ) return;
 #ifdef GS_QR_PROFILE
@@ -281,6 +287,7 @@ template <class T, int CPL> struct FastSolver {
         cnt = 0;
     }
     GS_DEV void publish(int end) {
+        if constexpr (LOG) return;
         if (!wantZ) return;
         const int b = sidx % RB;
         if (lane == 0) {
@@ -292,6 +299,7 @@ template <class T, int CPL> struct FastSolver {
         sidx += 1;
     }
     GS_DEV void ensure_space(int m) {
+        if constexpr (LOG) return;
         if (!wantZ) return;
         if (cnt + m > cap) {
             publish(0);
@@ -302,6 +310,11 @@ template <class T, int CPL> struct FastSolver {
     // make room for m ops once, so that the step loop can push without checking
     GS_DEV void reserve_ops(int) {}   // (the ring is small: every push checks for space, see push_*)
     GS_DEV void push_refl_c(int k, const C& tau1, const C& v2) {
+        if constexpr (LOG) {
+            lg.put_hdr(LOG_REFL, k, 1, k, r_const<R>(0.0), r_const<R>(0.0));
+            lg.put4(tau1.re, tau1.im, v2.re, v2.im);
+            return;
+        }
         if (!wantZ) return;
         if (cnt == cap) {
             publish(0);
@@ -321,6 +334,10 @@ template <class T, int CPL> struct FastSolver {
         cnt += 1;
     }
     GS_DEV void push_r(int op, int k, const R& a0, const R& a1, const R& a2) {
+        if constexpr (LOG) {
+            emit_r(op, k, a0, a1, a2);
+            return;
+        }
         if (!wantZ) return;
         if (cnt == cap) {
             publish(0);
@@ -339,6 +356,7 @@ template <class T, int CPL> struct FastSolver {
         cnt += 1;
     }
     GS_DEV void finish_ring() {
+        if constexpr (LOG) return;
         if (!wantZ) return;
         publish(1);
         // balance the outstanding "empty" arrivals of the last RB buffers
@@ -350,6 +368,10 @@ template <class T, int CPL> struct FastSolver {
     // complex single shift
     // ================================================================================================
     GS_DEV void emit_refl_c(int k, const C& tau1, const C& v2) {
+        if constexpr (LOG) {
+            push_refl_c(k, tau1, v2);
+            return;
+        }
         if (!wantZ) return;
         ensure_space(1);
         if (lane == 0) {
@@ -365,6 +387,10 @@ template <class T, int CPL> struct FastSolver {
         cnt += 1;
     }
     GS_DEV void emit_scale_c(int j0, int j1, const C& t) {
+        if constexpr (LOG) {
+            if (j1 >= j0) lg.put_hdr(LOG_SCALE, j0, 0, j1, t.re, t.im);
+            return;
+        }
         if (!wantZ || j1 < j0) return;
         ensure_space(1);
         if (lane == 0) {
@@ -694,16 +720,19 @@ template <class T, int CPL> struct FastSolver {
         C v2 = v1;
         R tau2 = tau1.re * v2.re - tau1.im * v2.im;   // Re(tau1 v2); tau1 v2 is real because the reflector's tail is
         C f_sub, f_diag;   // H[iend, iend-1], H[iend, iend] after the last step
-        const int capz = wantZ ? cap : 0x7fffffff;
-        const uint32_t ring32 = smem_u32(ring);
+        const int capz = (wantZ && !LOG) ? cap : 0x7fffffff;
+        const uint32_t ring32 = LOG ? 0u : smem_u32(ring);
+        if constexpr (LOG) lg.put_hdr(LOG_REFL, kf, iend - kf, iend, zero, zero);
 #ifdef GS_QR_PROFILE
         const long long tp2 = clock64();
         prof[2] += tp2 - tp1;
 #endif
         for (int k = kf;; ++k) {
-            if (cnt == capz) {
-                publish(0);
-                begin_buffer();
+            if constexpr (!LOG) {
+                if (cnt == capz) {
+                    publish(0);
+                    begin_buffer();
+                }
             }
             __syncwarp();
             const uint32_t kb = ES * (uint32_t)k;
@@ -770,10 +799,17 @@ template <class T, int CPL> struct FastSolver {
             const bool last = (k == iend - 1);
             {
                 const bool l0 = lane == 0;
-                const uint32_t re = ring32 + (uint32_t)sizeof(ZOp) * (uint32_t)(rbase + cnt);
-                sts_2i_if(re, (int)ZOP_REFL, k, l0 && wantZ);
-                sts_c64_if(re + 16, tau1, l0 && wantZ);
-                sts_c64_if(re + 32, v2, l0 && wantZ);
+                if constexpr (LOG) {
+                    const bool okl = lg.reserve();
+                    stg_2f64_if(lg.slot(), tau1.re, tau1.im, okl && l0);
+                    stg_2f64_if(lg.slot() + 16, v2.re, v2.im, okl && l0);
+                    if (okl) lg.advance();
+                } else {
+                    const uint32_t re = ring32 + (uint32_t)sizeof(ZOp) * (uint32_t)(rbase + cnt);
+                    sts_2i_if(re, (int)ZOP_REFL, k, l0 && wantZ);
+                    sts_c64_if(re + 16, tau1, l0 && wantZ);
+                    sts_c64_if(re + 32, v2, l0 && wantZ);
+                }
                 const uint32_t akm = ak - ES * (uint32_t)(k - 1 + EX);
                 const bool sub = l0 && (k > kf || store_sub);
                 sts_c64_if(akm + kb, mk_cx<R>(beta, zero), sub);
@@ -952,6 +988,9 @@ template <class T, int CPL> struct FastSolver {
                 st[0] += 1;
                 if constexpr (sizeof(R) == 8) sweep_complex_pipelined(t, istart, iend);
                 else sweep_complex(t, istart, iend);
+                if constexpr (LOG) {
+                    if (lg.ovf) return LOG_OVERFLOW_RC;   // the fused kernel redoes this matrix
+                }
                 // hand the sweep's reflectors to the Z-warp
                 publish(0);
                 begin_buffer();
@@ -973,6 +1012,15 @@ template <class T, int CPL> struct FastSolver {
     // real double shift
     // ================================================================================================
     GS_DEV void emit_r(int op, int k, const R& a0, const R& a1, const R& a2) {
+        if constexpr (LOG) {
+            if (op == ZOP_GIVENS) {
+                lg.put_hdr(LOG_GIVENS, k, 0, k, a0, a1);
+            } else {
+                lg.put_hdr(op == ZOP_REFL3 ? LOG_REFL3 : LOG_REFL2, k, 1, k, r_const<R>(0.0), r_const<R>(0.0));
+                lg.put4(a0, a1, a2, r_const<R>(0.0));
+            }
+            return;
+        }
         if (!wantZ) return;
         ensure_space(1);
         if (lane == 0) {
@@ -1209,15 +1257,18 @@ template <class T, int CPL> struct FastSolver {
         R beta = v0;
         R tau2 = tau1 * v1, tau3 = tau1 * v2;
         R L10 = zero, L20 = zero, L11 = zero, L21 = zero, L12 = zero, L22 = zero, L01 = zero, L02 = zero;
-        const int capz = wantZ ? cap : 0x7fffffff;
-        const uint32_t ring32 = smem_u32(ring);
+        const int capz = (wantZ && !LOG) ? cap : 0x7fffffff;
+        const uint32_t ring32 = LOG ? 0u : smem_u32(ring);
+        if constexpr (LOG) lg.put_hdr(LOG_REFL3, mx, iend - 1 - mx, iend, zero, zero);
 #ifdef GS_QR_PROFILE
         const long long tp2 = clock64();
 #endif
         for (int k = mx;; ++k) {
-            if (cnt == capz) {
-                publish(0);
-                begin_buffer();
+            if constexpr (!LOG) {
+                if (cnt == capz) {
+                    publish(0);
+                    begin_buffer();
+                }
             }
             __syncwarp();
             const uint32_t kb = ES * (uint32_t)k;
@@ -1286,11 +1337,18 @@ template <class T, int CPL> struct FastSolver {
             const bool last = (k == iend - 2);
             {
                 const bool l0 = lane == 0;
-                const uint32_t re = ring32 + (uint32_t)sizeof(ZOp) * (uint32_t)(rbase + cnt);
-                sts_2i_if(re, (int)ZOP_REFL3, k, l0 && wantZ);
-                sts_f64_if(re + 8, tau1, l0 && wantZ);
-                sts_f64_if(re + 16, v1, l0 && wantZ);
-                sts_f64_if(re + 24, v2, l0 && wantZ);
+                if constexpr (LOG) {
+                    const bool okl = lg.reserve();
+                    stg_2f64_if(lg.slot(), tau1, v1, okl && l0);
+                    stg_2f64_if(lg.slot() + 16, v2, zero, okl && l0);
+                    if (okl) lg.advance();
+                } else {
+                    const uint32_t re = ring32 + (uint32_t)sizeof(ZOp) * (uint32_t)(rbase + cnt);
+                    sts_2i_if(re, (int)ZOP_REFL3, k, l0 && wantZ);
+                    sts_f64_if(re + 8, tau1, l0 && wantZ);
+                    sts_f64_if(re + 16, v1, l0 && wantZ);
+                    sts_f64_if(re + 24, v2, l0 && wantZ);
+                }
                 const uint32_t akm = ak - ES * (uint32_t)(k - 1 + EX);
                 const bool sub = l0 && (k > mx);
                 sts_f64_if(akm + kb, beta, sub);
@@ -1504,6 +1562,9 @@ template <class T, int CPL> struct FastSolver {
                 st[0] += 1;
                 if constexpr (sizeof(T) == 8) sweep_real_pipelined(r1r, r1i, r2r, r2i, istart, iend);
                 else sweep_real(r1r, r1i, r2r, r2i, istart, iend);
+                if constexpr (LOG) {
+                    if (lg.ovf) return LOG_OVERFLOW_RC;
+                }
                 publish(0);
                 begin_buffer();
             }
@@ -1859,9 +1920,14 @@ __global__ void __launch_bounds__(64, qr_min_blocks<T, CPL>::value) gschur_qr_ke
     for (;;) {
         if (tid == 0) s_next = (long long)atomicAdd(p.counter, 1ULL);
         __syncthreads();
-        const long long b = s_next;
+        long long b = s_next;
         __syncthreads();
-        if (b >= p.batch) break;
+        if (p.list) {   // redo pass of the three-stage path: work item i is matrix list[i]
+            if (b >= (long long)*p.list_count) break;
+            b = p.list[b];
+        } else if (b >= p.batch) {
+            break;
+        }
         T* gA = reinterpret_cast<T*>(p.A) + b * p.strideA;
         F.Z = wantZ ? reinterpret_cast<T*>(p.Z) + b * p.strideZ : nullptr;
 

@@ -127,10 +127,11 @@ int enqueue_device(int kind, int mode, int n, int64_t batch, void* A, int lda, i
     DeviceState* ds = nullptr;
     int rc = device_state(dev, &ds);
     if (rc) return rc;
+    gs::stage_timing_begin_call();
     unsigned slot = ds->next.fetch_add(1) % kCounterRing;
     unsigned long long* counter = ds->counters + slot;
     CUDA_TRY(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), stream));
-    BatchedParams p;
+    BatchedParams p{};
     p.A = A;
     p.Z = Z;
     p.w = w;
@@ -482,11 +483,18 @@ const char* gschur_cuda_last_error(void) { return g_err.c_str(); }
 
 uint64_t gschur_cuda_launch_count(void) { return gs::launch_counter(); }
 
-// per-stage device times (ms) of the most recent two-kernel batched call while timing is enabled
-int gschur_cuda_stage_timing(int enable, float* ms_stage_a, float* ms_stage_b) {
+// per-stage device times (ms) of the most recent batched call while timing is enabled (summed over its sub-batches)
+int gschur_cuda_stage_timing3(int enable, float* ms_stage_a, float* ms_stage_b, float* ms_stage_c) {
     if (enable >= 0) gs::stage_timing_enable(enable != 0);
-    if (ms_stage_a && ms_stage_b) return gs::stage_timing_read(ms_stage_a, ms_stage_b);
+    if (ms_stage_a && ms_stage_b) return gs::stage_timing_read(ms_stage_a, ms_stage_b, ms_stage_c);
     return 0;
+}
+// two-value form: stage B here is everything after stage A (QR iteration + Z replay)
+int gschur_cuda_stage_timing(int enable, float* ms_stage_a, float* ms_stage_b) {
+    float c = 0.f;
+    int rc = gschur_cuda_stage_timing3(enable, ms_stage_a, ms_stage_b, &c);
+    if (rc == 0 && ms_stage_a && ms_stage_b) *ms_stage_b += c;
+    return rc;
 }
 
 int gschur_cuda_max_batched_n(int kind) {

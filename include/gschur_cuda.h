@@ -114,6 +114,12 @@ int gschur_cuda_measure_l2_bandwidth(double* gbs, double* ms);
  * -1 leaves it unchanged; when both pointers are given the times (ms) of the most recent call are returned.
  */
 int gschur_cuda_stage_timing(int enable, float* ms_stage_a, float* ms_stage_b);
+/*
+ * Three-value form for the three-stage path (n <= 64, Float64 / ComplexF64): stage A as above, stage B = QR iteration
+ * on H with the reflector log, stage C = replay of the log on the Schur vectors (+ the redo pass, normally empty).
+ * Times are summed over the sub-batches of the call.  The two-value form reports B + C as its stage B.
+ */
+int gschur_cuda_stage_timing3(int enable, float* ms_stage_a, float* ms_stage_b, float* ms_stage_c);
 
 /*
  * Batched Householder reduction to Hessenberg form, A_b = Q_b H_b Q_b^H.
