@@ -75,6 +75,14 @@ int device_state(int dev, DeviceState** out) {
                                              std::to_string(prop.major) + std::to_string(prop.minor));
         d.sm_count = prop.multiProcessorCount;
         CUDA_TRY(cudaMalloc(&d.counters, kCounterRing * sizeof(unsigned long long)));
+        // The stream-ordered allocations of the batched paths (scale info, reflector-log pool and page table: gigabytes
+        // per call) are kept in the device's default pool between calls instead of being returned to the driver at
+        // every synchronisation; gschur_cuda_release_workspace() trims the pool.
+        cudaMemPool_t mp = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&mp, dev) == cudaSuccess && mp) {
+            unsigned long long thr = ~0ULL;
+            cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+        }
         d.ok = true;
     }
     *out = &d;

@@ -12,6 +12,7 @@
 // regrouping of nothing — the same operations are applied to every row in the same order.
 #pragma once
 #include "fastqr.cuh"
+#include "chainqr.cuh"
 
 namespace gs {
 
@@ -176,17 +177,24 @@ template <class T> struct zreplay_layout {
     __host__ __device__ static size_t bytes(int n) { return off_pages(n) + 2 * (size_t)PAGE_BYTES; }
 };
 
-template <class T> struct ZReplay;
+// RPT = rows of Z per thread: independent rows interleave in one thread's instruction stream, which hides the
+// dependent-issue latency of the carried entry (4 FP64 operations deep per reflector) whatever the scheduler does.
+template <class T, int RPT> struct ZReplay;
 
 // ---- ComplexF64 ----
-template <> struct ZReplay<cx<double>> {
+template <int RPT> struct ZReplay<cx<double>, RPT> {
     typedef cx<double> T;
     int run, k;
-    T a;
-    GS_DEV void init() { run = 0; k = 0; a = mk_cx<double>(0.0, 0.0); }
-    // apply records [0, cnt) of the page at shared address `pg` to row `zr` (shared byte address of Z[r, 1]); cs = column
-    // stride in bytes
-    GS_DEV void page(uint32_t pg, int cnt, uint32_t zr, uint32_t cs) {
+    T a[RPT];
+    GS_DEV void init() {
+        run = 0;
+        k = 0;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) a[r] = mk_cx<double>(0.0, 0.0);
+    }
+    // apply records [0, cnt) of the page at shared address `pg` to the rows at shared byte addresses zr[] (of Z[r, 1]);
+    // cs = column stride in bytes
+    GS_DEV void page(uint32_t pg, int cnt, const uint32_t (&zr)[RPT], int nr, uint32_t cs) {
         int i = 0;
         while (i < cnt) {
             const uint32_t ra = pg + 32u * (uint32_t)i;
@@ -197,53 +205,64 @@ template <> struct ZReplay<cx<double>> {
                 if (op == LOG_REFL) {
                     run = count;
                     k = kk;
-                    a = lds_e<T>(zr + cs * (uint32_t)(k - 1));
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) a[r] = lds_e<T>(zr[r] + cs * (uint32_t)(k - 1));
                 } else {   // LOG_SCALE: columns kk..k2 times t
                     const T t = lds_e<T>(ra + 16);
                     for (int j = kk; j <= k2; ++j) {
-                        const uint32_t za = zr + cs * (uint32_t)(j - 1);
-                        sts_e<T>(za, lds_e<T>(za) * t);
+#pragma unroll
+                        for (int r = 0; r < RPT; ++r) {
+                            const uint32_t za = zr[r] + cs * (uint32_t)(j - 1);
+                            if (r < nr) sts_e<T>(za, lds_e<T>(za) * t);
+                        }
                     }
                 }
             } else {
                 const int m = (run < cnt - i) ? run : (cnt - i);
-                // software pipeline: record t+1 and column k+t+1 are fetched while reflector t is applied
-                T tau1n = lds_e<T>(ra), v2n = lds_e<T>(ra + 16);
-                uint32_t za = zr + cs * (uint32_t)k;          // column k+1 (1-based) of this row
-                T bn = lds_e<T>(za);
+                uint32_t zo = cs * (uint32_t)k;               // byte offset of column k+1 (1-based)
+                uint32_t rr = ra;
                 for (int t = 0; t < m; ++t) {
-                    const T tau1 = tau1n, v2 = v2n, b = bn;
-                    const uint32_t rn = ra + 32u * (uint32_t)((t + 1 < m) ? t + 1 : t);
-                    const uint32_t zn = (t + 1 < m) ? za + cs : za;
-                    tau1n = lds_e<T>(rn);
-                    v2n = lds_e<T>(rn + 16);
-                    bn = lds_e<T>(zn);
+                    const T tau1 = lds_e<T>(rr), v2 = lds_e<T>(rr + 16);
+                    T b[RPT];
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) b[r] = lds_e<T>(zr[r] + zo);
                     const double tau2 = tau1.re * v2.re - tau1.im * v2.im;
-                    // ss = tau1 a + tau2 b;  Z[r,k] = a - ss;  a <- b - ss conj(v2)      (src/GenericSchur.jl:455-459)
-                    T ss;
-                    ss.re = fma(tau1.re, a.re, fma(-tau1.im, a.im, tau2 * b.re));
-                    ss.im = fma(tau1.re, a.im, fma(tau1.im, a.re, tau2 * b.im));
-                    sts_e<T>(za - cs, a - ss);
-                    a = e_fnma_cjb(ss, v2, b);
-                    za = zn;
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        // ss = tau1 a + tau2 b;  Z[r,k] = a - ss;  a <- b - ss conj(v2)      (src/GenericSchur.jl:455-459)
+                        T ss;
+                        ss.re = fma(tau1.re, a[r].re, fma(-tau1.im, a[r].im, tau2 * b[r].re));
+                        ss.im = fma(tau1.re, a[r].im, fma(tau1.im, a[r].re, tau2 * b[r].im));
+                        if (r < nr) sts_e<T>(zr[r] + zo - cs, a[r] - ss);
+                        a[r] = e_fnma_cjb(ss, v2, b[r]);
+                    }
+                    zo += cs;
+                    rr += 32u;
                 }
-                // after the loop za points at the column of the last b (when m >= 1)
                 i += m;
                 k += m;
                 run -= m;
-                if (run == 0) sts_e<T>(zr + cs * (uint32_t)(k - 1), a);
+                if (run == 0) {
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) if (r < nr) sts_e<T>(zr[r] + cs * (uint32_t)(k - 1), a[r]);
+                }
             }
         }
     }
 };
 
 // ---- Float64 ----
-template <> struct ZReplay<double> {
+template <int RPT> struct ZReplay<double, RPT> {
     typedef double T;
     int run, k;
-    double z1, z2;
-    GS_DEV void init() { run = 0; k = 0; z1 = z2 = 0.0; }
-    GS_DEV void page(uint32_t pg, int cnt, uint32_t zr, uint32_t cs) {
+    double z1[RPT], z2[RPT];
+    GS_DEV void init() {
+        run = 0;
+        k = 0;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) z1[r] = z2[r] = 0.0;
+    }
+    GS_DEV void page(uint32_t pg, int cnt, const uint32_t (&zr)[RPT], int nr, uint32_t cs) {
         int i = 0;
         while (i < cnt) {
             const uint32_t ra = pg + 32u * (uint32_t)i;
@@ -251,72 +270,83 @@ template <> struct ZReplay<double> {
                 int op, kk, count, k2;
                 asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(op), "=r"(kk), "=r"(count), "=r"(k2) : "r"(ra));
                 (void)k2;
+                i += 1;
                 if (op == LOG_REFL3) {
-                    i += 1;
                     run = count;
                     k = kk;
-                    z1 = lds_e<T>(zr + cs * (uint32_t)(k - 1));
-                    z2 = lds_e<T>(zr + cs * (uint32_t)k);
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        z1[r] = lds_e<T>(zr[r] + cs * (uint32_t)(k - 1));
+                        z2[r] = lds_e<T>(zr[r] + cs * (uint32_t)k);
+                    }
                 } else if (op == LOG_REFL2) {
-                    // header + one payload record; the payload may sit on the next page: handled as a run of length 1
-                    i += 1;
+                    // header + one payload record (which may sit on the next page): a pending run of length -1
                     run = -1;
                     k = kk;
                 } else {   // LOG_GIVENS (cs, sn) on columns kk, kk+1
-                    i += 1;
                     const double c = lds_e<T>(ra + 16), s = lds_e<T>(ra + 24);
-                    const uint32_t za = zr + cs * (uint32_t)(kk - 1);
-                    const double a1 = lds_e<T>(za), a2 = lds_e<T>(za + cs);
-                    sts_e<T>(za, a1 * c + a2 * s);
-                    sts_e<T>(za + cs, -a1 * s + a2 * c);
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        const uint32_t za = zr[r] + cs * (uint32_t)(kk - 1);
+                        const double a1 = lds_e<T>(za), a2 = lds_e<T>(za + cs);
+                        if (r < nr) sts_e<T>(za, a1 * c + a2 * s);
+                        if (r < nr) sts_e<T>(za + cs, -a1 * s + a2 * c);
+                    }
                 }
             } else if (run < 0) {   // the payload of a two-row reflector
                 const double tau1 = lds_e<T>(ra), v2 = lds_e<T>(ra + 8);
                 const double tau2 = tau1 * v2;
-                const uint32_t za = zr + cs * (uint32_t)(k - 1);
-                const double x = lds_e<T>(za), y = lds_e<T>(za + cs);
-                const double ss = x + v2 * y;
-                sts_e<T>(za, x - ss * tau1);
-                sts_e<T>(za + cs, y - ss * tau2);
+#pragma unroll
+                for (int r = 0; r < RPT; ++r) {
+                    const uint32_t za = zr[r] + cs * (uint32_t)(k - 1);
+                    const double x = lds_e<T>(za), y = lds_e<T>(za + cs);
+                    const double ss = x + v2 * y;
+                    if (r < nr) sts_e<T>(za, x - ss * tau1);
+                    if (r < nr) sts_e<T>(za + cs, y - ss * tau2);
+                }
                 i += 1;
                 run = 0;
             } else {
                 const int m = (run < cnt - i) ? run : (cnt - i);
-                double t1n = lds_e<T>(ra), v2n = lds_e<T>(ra + 8), v3n = lds_e<T>(ra + 16);
-                uint32_t za = zr + cs * (uint32_t)(k + 1);    // column k+2 (1-based) of this row
-                double z3n = lds_e<T>(za);
+                uint32_t zo = cs * (uint32_t)(k + 1);         // byte offset of column k+2 (1-based)
+                uint32_t rr = ra;
                 for (int t = 0; t < m; ++t) {
-                    const double tau1 = t1n, v2 = v2n, v3 = v3n, z3 = z3n;
-                    const uint32_t rn = ra + 32u * (uint32_t)((t + 1 < m) ? t + 1 : t);
-                    const uint32_t zn = (t + 1 < m) ? za + cs : za;
-                    t1n = lds_e<T>(rn);
-                    v2n = lds_e<T>(rn + 8);
-                    v3n = lds_e<T>(rn + 16);
-                    z3n = lds_e<T>(zn);
+                    const double tau1 = lds_e<T>(rr), v2 = lds_e<T>(rr + 8), v3 = lds_e<T>(rr + 16);
+                    double z3[RPT];
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) z3[r] = lds_e<T>(zr[r] + zo);
                     const double tau2 = tau1 * v2, tau3 = tau1 * v3;
-                    const double ss = z1 + v2 * z2 + v3 * z3;                    // src/GenericSchur.jl:920-925
-                    sts_e<T>(za - 2 * cs, z1 - ss * tau1);
-                    z1 = z2 - ss * tau2;
-                    z2 = z3 - ss * tau3;
-                    za = zn;
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        const double ss = z1[r] + v2 * z2[r] + v3 * z3[r];           // src/GenericSchur.jl:920-925
+                        if (r < nr) sts_e<T>(zr[r] + zo - 2 * cs, z1[r] - ss * tau1);
+                        z1[r] = z2[r] - ss * tau2;
+                        z2[r] = z3[r] - ss * tau3;
+                    }
+                    zo += cs;
+                    rr += 32u;
                 }
                 i += m;
                 k += m;
                 run -= m;
                 if (run == 0) {
-                    sts_e<T>(zr + cs * (uint32_t)(k - 1), z1);
-                    sts_e<T>(zr + cs * (uint32_t)k, z2);
+#pragma unroll
+                    for (int r = 0; r < RPT; ++r) {
+                        if (r < nr) sts_e<T>(zr[r] + cs * (uint32_t)(k - 1), z1[r]);
+                        if (r < nr) sts_e<T>(zr[r] + cs * (uint32_t)k, z2[r]);
+                    }
                 }
             }
         }
     }
 };
 
-template <class T> __global__ void __launch_bounds__(64) gschur_zreplay_kernel(BatchedParams p) {
+// NT threads per CTA, RPT rows per thread: NT * RPT >= n
+template <class T, int NT, int RPT> __global__ void __launch_bounds__(NT) gschur_zreplay_kernel(BatchedParams p) {
     typedef zreplay_layout<T> ZL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n;
-    const int tid = threadIdx.x, NT = blockDim.x;
+    const int tid = threadIdx.x;
     T* Zs = reinterpret_cast<T*>(smem_raw);
     const uint32_t zs32 = smem_u32(Zs);
     const uint32_t pg32 = smem_u32(smem_raw + ZL::off_pages(n));
@@ -339,10 +369,18 @@ template <class T> __global__ void __launch_bounds__(64) gschur_zreplay_kernel(B
             const int i = e % n, j = e / n;
             Zs[e] = gZ[i + (size_t)j * p.ldz];
         }
-        ZReplay<T> RP;
+        ZReplay<T, RPT> RP;
         RP.init();
+        // rows tid, tid + NT, ...: nr of them exist; the others read row 0 and never store
         const bool act = tid < n;
-        const uint32_t zr = zs32 + (uint32_t)sizeof(T) * (uint32_t)(act ? tid : 0);
+        int nr = 0;
+        uint32_t zr[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int rowi = tid + NT * r;
+            nr += rowi < n ? 1 : 0;
+            zr[r] = zs32 + (uint32_t)sizeof(T) * (uint32_t)(rowi < n ? rowi : 0);
+        }
         const uint32_t cs = (uint32_t)sizeof(T) * (uint32_t)n;
         for (int pgi = 0; pgi < npages; ++pgi) {
             if (pgi + 1 < npages) {
@@ -353,7 +391,7 @@ template <class T> __global__ void __launch_bounds__(64) gschur_zreplay_kernel(B
             }
             __syncthreads();
             const int cnt = (nrec - pgi * LOG_PAGE_REC < LOG_PAGE_REC) ? nrec - pgi * LOG_PAGE_REC : LOG_PAGE_REC;
-            if (act) RP.page(pg32 + (uint32_t)((pgi & 1) * PB), cnt, zr, cs);
+            if (act) RP.page(pg32 + (uint32_t)((pgi & 1) * PB), cnt, zr, nr, cs);
             __syncthreads();
         }
         for (int e = tid; e < n * n; e += NT) {
@@ -362,6 +400,34 @@ template <class T> __global__ void __launch_bounds__(64) gschur_zreplay_kernel(B
         }
         __syncthreads();
     }
+}
+
+// stage C variants by size: threads per CTA and rows per thread
+struct StageCKernel {
+    void (*fn)(BatchedParams);
+    int threads;
+};
+template <class T> StageCKernel stage_c_select(int n) {
+    StageCKernel k;
+    constexpr bool CX = etraits<T>::is_complex;
+    if (n <= 32) {
+        k.fn = gschur_zreplay_kernel<T, 32, 1>;
+        k.threads = 32;
+    } else if (CX) {
+        // 64 x 64 ComplexF64: Z is 64 KB, three CTAs per SM — one warp with two rows per thread each (GSCHUR_ZRPT=1: two warps)
+        const char* e = std::getenv("GSCHUR_ZRPT");
+        if (e && e[0] == '1') {
+            k.fn = gschur_zreplay_kernel<T, 64, 1>;
+            k.threads = 64;
+        } else {
+            k.fn = gschur_zreplay_kernel<T, 32, 2>;
+            k.threads = 32;
+        }
+    } else {
+        k.fn = gschur_zreplay_kernel<T, 64, 1>;
+        k.threads = 64;
+    }
+    return k;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -376,6 +442,37 @@ inline size_t log_pool_budget_bytes() {
     size_t fr = 0, tot = 0;
     if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && fr / 2 < budget) budget = fr / 2;
     return budget;
+}
+
+// stage B variants: kernel, dynamic shared memory, matrices per (one-warp) CTA
+struct StageBKernel {
+    void (*fn)(BatchedParams);
+    size_t smem;
+    int per_cta;
+    const char* name;
+};
+template <class T, int CPL> StageBKernel stage_b_select(int n) {
+    StageBKernel k;
+    k.fn = gschur_qrlog_kernel<T, CPL>;
+    k.smem = fast_smem_layout<T, CPL>::off_ring(n);
+    k.per_cta = 1;
+    k.name = "qrlog";
+    // GSCHUR_CHAIN = 0: first-generation logging kernel; 32 / 16: lanes per matrix of the chain kernel (chainqr.cuh)
+    const char* sel = std::getenv("GSCHUR_CHAIN");
+    const int lpm = sel ? std::atoi(sel) : 32;
+    constexpr bool CX = std::is_same<T, cx<double>>::value;
+    if (lpm == 32) {
+        k.fn = gschur_chain_kernel<T, 32, CPL, (CX ? (CPL == 1 ? 12 : 6) : (CPL == 1 ? 16 : 12))>;
+        k.smem = chain_layout<T, 32, CPL>::bytes(n);
+        k.per_cta = 1;
+        k.name = "chain32";
+    } else if (lpm == 16) {
+        k.fn = gschur_chain_kernel<T, 16, 2 * CPL, (CX ? (CPL == 1 ? 10 : 3) : (CPL == 1 ? 12 : 6))>;
+        k.smem = chain_layout<T, 16, 2 * CPL>::bytes(n);
+        k.per_cta = 2;
+        k.name = "chain16";
+    }
+    return k;
 }
 
 template <class T, int CPL> int launch_fast3(const BatchedParams& p_in, int dev_sms, cudaStream_t stream, std::string* err) {
@@ -431,10 +528,12 @@ template <class T, int CPL> int launch_fast3(const BatchedParams& p_in, int dev_
         F3_TRY(cudaMallocAsync((void**)&table, (size_t)sub * (2 + maxp) * sizeof(int), stream), "cudaMallocAsync(log table)");
     }
     {
-        auto kB = gschur_qrlog_kernel<T, CPL>;
-        auto kC = gschur_zreplay_kernel<T>;
+        const StageBKernel sb = stage_b_select<T, CPL>(n);
+        auto kB = sb.fn;
+        const StageCKernel sc = stage_c_select<T>(n);
+        auto kC = sc.fn;
         auto kR = gschur_qr_kernel<T, CPL>;
-        const size_t smemB = fast_smem_layout<T, CPL>::off_ring(n);
+        const size_t smemB = sb.smem;
         const size_t smemC = zreplay_layout<T>::bytes(n);
         const size_t smemR = fast_smem_layout<T, CPL>::bytes(n);
         int perB = 0, perR = 0;
@@ -485,12 +584,12 @@ template <class T, int CPL> int launch_fast3(const BatchedParams& p_in, int dev_
             stage_timing_mark(1, stream);
             p.counter = ctr;
             long long grid = (long long)perB * dev_sms;
-            if (grid > cn) grid = cn;
+            if (grid > (cn + sb.per_cta - 1) / sb.per_cta) grid = (cn + sb.per_cta - 1) / sb.per_cta;
             kB<<<(unsigned)grid, 32, smemB, stream>>>(p);
             note_launch();
             stage_timing_mark(2, stream);
             if (wantZ) {
-                kC<<<(unsigned)(cn < 0x7fffffffLL ? cn : 0x7fffffffLL), n <= 32 ? 32 : 64, smemC, stream>>>(p);
+                kC<<<(unsigned)(cn < 0x7fffffffLL ? cn : 0x7fffffffLL), sc.threads, smemC, stream>>>(p);
                 note_launch();
             }
             // redo pass: matrices whose log overflowed (none for ordinary input: every CTA exits at once)

@@ -39,7 +39,8 @@ GS_DEV void stg_4i_if(void* a, int x, int y, int z, int w, bool p) {
                  : "memory");
 }
 
-// Producer side (one warp, state uniform across the lanes; lane 0 stores).
+// Producer side.  One "slot" of a warp (all 32 lanes, or an aligned group of 16 / 8 lanes when a warp works on several
+// matrices at once) writes the log of one matrix: the state is uniform across the slot's lanes, the leader lane stores.
 template <class R> struct LogWriter {
     static constexpr int REC = 4 * (int)sizeof(R);
     static constexpr int PAGE_BYTES = LOG_PAGE_REC * REC;
@@ -49,20 +50,26 @@ template <class R> struct LogWriter {
     int* row;
     int maxp;
     unsigned char* cur;
-    int left, nrec, npg, lane;
+    int left, nrec, npg;
+    unsigned mask;     // lanes of the slot
+    int leader;        // first lane of the slot
+    bool lead;         // this lane is the leader
     bool on, ovf;
 
-    GS_DEV void init(const BatchedParams& p, long long b, int lane_, bool enable) {
+    GS_DEV void init(const BatchedParams& p, long long b, int lane, bool enable, unsigned slot_mask = 0xffffffffu,
+                     int leader_lane = 0) {
         pool = p.log_pool;
         next = p.log_next;
         npages = p.log_pages;
         maxp = p.log_maxp;
-        row = p.log_table ? p.log_table + b * (long long)(2 + p.log_maxp) : nullptr;
+        row = (p.log_table && enable) ? p.log_table + b * (long long)(2 + p.log_maxp) : nullptr;
         cur = nullptr;
         left = 0;
         nrec = 0;
         npg = 0;
-        lane = lane_;
+        mask = slot_mask;
+        leader = leader_lane;
+        lead = lane == leader_lane;
         on = enable && p.log_pool != nullptr;
         ovf = false;
     }
@@ -72,18 +79,18 @@ template <class R> struct LogWriter {
             return;
         }
         unsigned pg = 0;
-        if (lane == 0) pg = atomicAdd(next, 1u);
-        pg = __shfl_sync(0xffffffffu, pg, 0);
+        if (lead) pg = atomicAdd(next, 1u);
+        pg = __shfl_sync(mask, pg, leader);
         if (pg >= npages) {
             ovf = true;
             return;
         }
-        if (lane == 0) row[2 + npg] = (int)pg;
+        if (lead) row[2 + npg] = (int)pg;
         npg += 1;
         cur = pool + (size_t)pg * PAGE_BYTES;
         left = LOG_PAGE_REC;
     }
-    // the caller stores the record at `slot()` (lane 0) and then calls `advance()`
+    // the caller stores the record at `slot()` (leader lane) and then calls `advance()`
     GS_DEV bool reserve() {   // returns true when the record may be stored
         if (!on || ovf) return false;
         if (left == 0) new_page();
@@ -97,7 +104,7 @@ template <class R> struct LogWriter {
     }
     GS_DEV void put_hdr(int op, int k, int count, int k2, const R& x, const R& y) {
         if (!reserve()) return;
-        if (lane == 0) {
+        if (lead) {
             int* h = reinterpret_cast<int*>(cur);
             h[0] = op;
             h[1] = k;
@@ -111,7 +118,7 @@ template <class R> struct LogWriter {
     }
     GS_DEV void put4(const R& a0, const R& a1, const R& a2, const R& a3) {
         if (!reserve()) return;
-        if (lane == 0) {
+        if (lead) {
             R* a = reinterpret_cast<R*>(cur);
             a[0] = a0;
             a[1] = a1;
@@ -121,7 +128,7 @@ template <class R> struct LogWriter {
         advance();
     }
     GS_DEV void finish() {
-        if (row && lane == 0) {
+        if (row && lead) {
             row[0] = on ? nrec : 0;
             row[1] = ovf ? 1 : 0;
         }

@@ -6,6 +6,8 @@
 #include <cstdlib>
 #include <vector>
 #include <random>
+#include <complex>
+#include <cmath>
 #include "qr3.cuh"
 using namespace gs;
 #ifndef DEV_REAL
@@ -62,6 +64,52 @@ int main(int argc, char** argv) {
         stage_timing_read(&a, &b, &c);
         printf("rc=%d %s %s | n=%d batch=%lld: total %.2f ms  A %.2f  B %.2f  C %.2f  -> %.0f matrices/s\n", rc, err.c_str(),
                cudaGetErrorString(ce), n, batch, ms, a, b, c, batch / ms * 1e3);
+    }
+    // ---- residuals of a few matrices on the host (plain Float64): ||A - Z T Z'||_F / (n eps ||A||_F), ||Z'Z - I||_F / (n eps) ----
+    {
+        const int nchk = batch < 4 ? (int)batch : 4;
+        const size_t m = (size_t)n * n;
+        std::vector<ET> T(m), Z(m);
+        typedef std::complex<double> cd;
+        for (int c = 0; c < nchk; ++c) {
+            const long long b = (c == 0) ? 0 : (c == 1 ? batch - 1 : (batch / 2 + c));
+            cudaMemcpy(T.data(), dA + b * m, m * sizeof(ET), cudaMemcpyDeviceToHost);
+            cudaMemcpy(Z.data(), dZ + b * m, m * sizeof(ET), cudaMemcpyDeviceToHost);
+            auto get = [&](const ET* M, int i, int j) -> cd {
+#ifndef DEV_REAL
+                return cd(M[i + (size_t)j * n].re, M[i + (size_t)j * n].im);
+#else
+                return cd(M[i + (size_t)j * n], 0.0);
+#endif
+            };
+            std::vector<cd> ZT(m), R(m);
+            double na = 0, nr = 0, no = 0, low = 0;
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) {
+                    cd s = 0;
+                    for (int k = 0; k < n; ++k) s += get(Z.data(), i, k) * get(T.data(), k, j);
+                    ZT[i + (size_t)j * n] = s;
+                }
+            for (int i = 0; i < n; ++i)
+                for (int j = 0; j < n; ++j) {
+                    cd s = 0, o = 0;
+                    for (int k = 0; k < n; ++k) {
+                        s += ZT[i + (size_t)k * n] * std::conj(get(Z.data(), j, k));
+                        o += std::conj(get(Z.data(), k, i)) * get(Z.data(), k, j);
+                    }
+                    const cd a = get(hA.data() + b * m, i, j);
+                    na += std::norm(a);
+                    nr += std::norm(a - s);
+                    no += std::norm(o - (i == j ? 1.0 : 0.0));
+#ifndef DEV_REAL
+                    if (i > j) low += std::abs(get(T.data(), i, j));
+#else
+                    if (i > j + 1) low += std::abs(get(T.data(), i, j));
+#endif
+                }
+            const double eps = 2.220446049250313e-16;
+            printf("matrix %lld: backward %.3f  orth %.3f  below-triangle %.1e\n", b, std::sqrt(nr / na) / (n * eps), std::sqrt(no) / (n * eps), low);
+        }
     }
     std::vector<unsigned> st(batch * 4);
     std::vector<int> info(batch);
