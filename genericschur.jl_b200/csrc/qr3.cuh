@@ -13,6 +13,7 @@
 #pragma once
 #include "fastqr.cuh"
 #include "chainqr.cuh"
+#include "zreg.cuh"
 
 namespace gs {
 
@@ -402,14 +403,34 @@ template <class T, int NT, int RPT> __global__ void __launch_bounds__(NT) gschur
     }
 }
 
-// stage C variants by size: threads per CTA and rows per thread
+// stage C variants by size: kernel, threads per CTA, dynamic shared memory
 struct StageCKernel {
     void (*fn)(BatchedParams);
     int threads;
+    size_t smem;
+    const char* name;
 };
 template <class T> StageCKernel stage_c_select(int n) {
     StageCKernel k;
     constexpr bool CX = etraits<T>::is_complex;
+    // GSCHUR_ZREG=0: first-generation replay (Z in shared memory); default: rows of Z in registers (zreg.cuh)
+    const char* zsel = std::getenv("GSCHUR_ZREG");
+    if (!(zsel && zsel[0] == '0')) {
+        if (n <= 32) {
+            k.fn = gschur_zreg_kernel<T, 32, 32, (CX ? 12 : 16)>;
+            k.threads = 32;
+            k.smem = zreg_layout<T, 32, 32>::bytes();
+        } else {
+            constexpr int NREG = CX ? 32 : 64;   // ComplexF64: the leading 32 columns stay in shared memory
+            k.fn = gschur_zreg_kernel<T, 64, NREG, 6>;
+            k.threads = 64;
+            k.smem = zreg_layout<T, 64, NREG>::bytes();
+        }
+        k.name = "zreg";
+        return k;
+    }
+    k.smem = zreplay_layout<T>::bytes(n);
+    k.name = "zreplay";
     if (n <= 32) {
         k.fn = gschur_zreplay_kernel<T, 32, 1>;
         k.threads = 32;
@@ -534,7 +555,7 @@ template <class T, int CPL> int launch_fast3(const BatchedParams& p_in, int dev_
         auto kC = sc.fn;
         auto kR = gschur_qr_kernel<T, CPL>;
         const size_t smemB = sb.smem;
-        const size_t smemC = zreplay_layout<T>::bytes(n);
+        const size_t smemC = sc.smem;
         const size_t smemR = fast_smem_layout<T, CPL>::bytes(n);
         int perB = 0, perR = 0;
         F3_TRY(cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB), "qrlog kernel setup");
