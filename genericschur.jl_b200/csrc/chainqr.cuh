@@ -1025,11 +1025,12 @@ template <int LPM, int CPL> struct ChainR {
 // ---------------------------------------------------------------------------------------------------------------------
 // kernel: one warp per CTA, 32 / LPM matrices per warp
 // ---------------------------------------------------------------------------------------------------------------------
-template <class T, int LPM, int CPL> struct chain_traits;
-template <int LPM, int CPL> struct chain_traits<cx<double>, LPM, CPL> {
+// VAR = 0: the chain solvers of this file; VAR = 1: the owner-computes solvers of ownqr.cuh (LPM = 32 only)
+template <class T, int LPM, int CPL, int VAR = 0> struct chain_traits;
+template <int LPM, int CPL> struct chain_traits<cx<double>, LPM, CPL, 0> {
     typedef ChainC<LPM, CPL> Solver;
 };
-template <int LPM, int CPL> struct chain_traits<double, LPM, CPL> {
+template <int LPM, int CPL> struct chain_traits<double, LPM, CPL, 0> {
     typedef ChainR<LPM, CPL> Solver;
 };
 
@@ -1040,12 +1041,12 @@ template <class T, int LPM, int CPL> struct chain_layout {
     __host__ __device__ static size_t bytes(int n) { return NS * slot_bytes(n); }
 };
 
-template <class T, int LPM, int CPL, int MINB>
+template <class T, int LPM, int CPL, int MINB, int VAR = 0>
 __global__ void __launch_bounds__(32, MINB) gschur_chain_kernel(BatchedParams p) {
     typedef typename etraits<T>::real R;
     typedef cx<R> C;
     constexpr bool CPLX = etraits<T>::is_complex;
-    typedef typename chain_traits<T, LPM, CPL>::Solver S;
+    typedef typename chain_traits<T, LPM, CPL, VAR>::Solver S;
     typedef chain_layout<T, LPM, CPL> CL;
     constexpr int NS = CL::NS;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -13,6 +13,7 @@
 #pragma once
 #include "fastqr.cuh"
 #include "chainqr.cuh"
+#include "ownqr.cuh"
 #include "zreg.cuh"
 
 namespace gs {
@@ -478,15 +479,21 @@ template <class T, int CPL> StageBKernel stage_b_select(int n) {
     k.smem = fast_smem_layout<T, CPL>::off_ring(n);
     k.per_cta = 1;
     k.name = "qrlog";
-    // GSCHUR_CHAIN = 0: first-generation logging kernel; 32 / 16: lanes per matrix of the chain kernel (chainqr.cuh)
+    // GSCHUR_CHAIN = 1 (default): owner-computes sweeps (ownqr.cuh); 32 / 16: lanes per matrix of the chain kernels
+    // (chainqr.cuh); 0: first-generation logging kernel
     const char* sel = std::getenv("GSCHUR_CHAIN");
-    const int lpm = sel ? std::atoi(sel) : 32;
+    const int lpm = sel ? std::atoi(sel) : 1;
     constexpr bool CX = std::is_same<T, cx<double>>::value;
     if (lpm == 32) {
         k.fn = gschur_chain_kernel<T, 32, CPL, (CX ? (CPL == 1 ? 12 : 6) : (CPL == 1 ? 16 : 12))>;
         k.smem = chain_layout<T, 32, CPL>::bytes(n);
         k.per_cta = 1;
         k.name = "chain32";
+    } else if (lpm == 1) {   // owner-computes sweeps (ownqr.cuh)
+        k.fn = gschur_chain_kernel<T, 32, CPL, (CX ? (CPL == 1 ? 12 : 6) : (CPL == 1 ? 16 : 12)), 1>;
+        k.smem = chain_layout<T, 32, CPL>::bytes(n);
+        k.per_cta = 1;
+        k.name = "own";
     } else if (lpm == 16) {
         k.fn = gschur_chain_kernel<T, 16, 2 * CPL, (CX ? (CPL == 1 ? 10 : 3) : (CPL == 1 ? 12 : 6))>;
         k.smem = chain_layout<T, 16, 2 * CPL>::bytes(n);
