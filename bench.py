@@ -136,7 +136,8 @@ def cpu_baseline(kind, n, batch, seed, cores=None, steps=1):
         best = dt if best is None else min(best, dt)
     return {"value": sample / best, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{sample} of the {batch} matrices ({n}x{n}, same generator/seed), {cores} host threads, "
-                      f"oracle/ C++ restatement of gschur! (Julia is not installed; see DESIGN.md)"}, sample, best
+                      f"oracle/ C++ restatement of gschur! built with -O2 -ffp-contract=off (Julia's no-contraction "
+                      f"semantics; Julia is not installed, see DESIGN.md)"}, sample, best
 
 
 def other_workloads(gs, torch, skip):
@@ -161,7 +162,7 @@ def other_workloads(gs, torch, skip):
         return best
 
     for name, (kind, n, batch, flops, desc) in WORKLOADS.items():
-        if name == skip:
+        if name == skip or name == "f64n64":     # the Float64 n = 64 batch is a first-class record (measure_workload)
             continue
         dt = torch.complex128 if kind == 1 else torch.float64
         A0 = torch.rand((batch, n, n), dtype=dt, device="cuda")
@@ -276,56 +277,43 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
-    ap.add_argument("--batch", type=int, default=0, help="override the per-GPU batch (development only)")
-    ap.add_argument("--e2e-steps", type=int, default=5)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-others", action="store_true", help="skip the informational runs of the other BASELINE configs")
-    args = ap.parse_args()
-    if args.warmup < 3:
-        args.warmup = 3
-    if args.impl == "reference":
-        run_reference(args)
-        return
+def kernel_traffic(kind, n):
+    """DRAM / L2 bytes per matrix of the dominant kernel from the committed ncu summary profiles/kernel_traffic.json
+    (written by scripts/ncu_traffic.py from `ncu --set full` captures; each entry names kernel, capture and git sha)."""
+    path = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    try:
+        with open(path) as f:
+            db = json.load(f)
+    except (OSError, ValueError):
+        return None
+    key = f"stageB_{'c64' if kind == 1 else 'f64'}_n{n}"
+    return db.get(key)
 
-    import torch
-    import torch.distributed as dist
 
-    gs = load_package()
-    kind, n, batch, flops_per_matrix, desc = WORKLOADS[args.workload]
+def measure_workload(gs, torch, dist, args, name, world, rank, local_rank, with_e2e=True, with_pageable=False):
+    """Device-resident throughput (CUDA events on the launching stream, max over ranks), per-stage kernel times, roofline
+    and the end-to-end figure through the host API for one workload.  Returns (record, clocks, launches, wall)."""
+    import ctypes
+    from genericschur_jl_b200 import _lib as _gl
+    _L = _gl.lib()
+    kind, n, batch, flops_per_matrix, desc = WORKLOADS[name]
     if args.batch:
         batch = args.batch
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        # a bare `python bench.py --gpus N` without torchrun runs as one rank
-        world = max(world, 1)
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device: the Schur path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    total = batch * (1 if args.scaling == "strong" else world)
+    if args.scaling == "strong":
+        lo, hi = shard_bounds(batch, world, rank)
+        batch = hi - lo
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- inputs: this rank's shard (weak scaling: `batch` matrices per GPU), resident in HBM -------------------
     seed = 1234 + 3 + 1000 * rank
     A_host_np = make_inputs(kind, n, batch, seed)
     tdt = torch.complex128 if kind == 1 else torch.float64
     esz = 16 if kind == 1 else 8
-    # torch views of the Fortran-ordered numpy data: shape (batch, n, n) C-order == (n, n, batch) F-order in memory
-    A_host = torch.from_numpy(A_host_np.T)            # (batch, n, n) view, contiguous
+    A_host = torch.from_numpy(A_host_np.T)            # (batch, n, n) view == (n, n, batch) Fortran order in memory
     assert A_host.is_contiguous()
     A0 = A_host.cuda()
     A = torch.empty_like(A0)
@@ -339,9 +327,6 @@ def main():
         gs.gschur_device_(kind, n, batch, A.data_ptr(), Z.data_ptr(), w.data_ptr(), info.data_ptr(),
                           stats.data_ptr(), scale=True, stream=stream)
 
-    import ctypes
-    from genericschur_jl_b200 import _lib as _gl
-    _L = _gl.lib()
     for _ in range(args.warmup):
         A.copy_(A0)
         step()
@@ -366,122 +351,200 @@ def main():
     launches = gs.launch_count() - launches0
     step_ms = [a.elapsed_time(b) for a, b in evs]
     total_ms = float(sum(step_ms))
-    # per-kernel device times of one more (untimed) step: stage A = gehrd_q_kernel, stage B = gschur_qr_kernel
-    _L.gschur_cuda_stage_timing(1, None, None)
+    # per-stage device times of one more (untimed) step: CUDA events recorded by the library on the launching stream
+    _L.gschur_cuda_stage_timing3(1, None, None, None)
     A.copy_(A0)
     step()
-    ms_a, ms_b = ctypes.c_float(0), ctypes.c_float(0)
-    have_stage = _L.gschur_cuda_stage_timing(0, ctypes.byref(ms_a), ctypes.byref(ms_b)) == 0
+    ms_a, ms_b, ms_c = ctypes.c_float(0), ctypes.c_float(0), ctypes.c_float(0)
+    have_stage = _L.gschur_cuda_stage_timing3(0, ctypes.byref(ms_a), ctypes.byref(ms_b), ctypes.byref(ms_c)) == 0
     torch.cuda.synchronize()
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = world * batch / (ms_per_step * 1e-3)
+    value = total / (ms_per_step * 1e-3)
     assert int((info != 0).sum().item()) == 0
+    # size-independent invariants of the timed result on the whole batch (device side, cheap): T (quasi-)triangular
+    # below the sub-diagonal, trace(T) == sum(w) to rounding
+    # storage is (batch, column, row): A[b, j, i] = T_b[i, j], so "below the (sub-)diagonal of T" is triu of A[b]
+    low = torch.triu(A, diagonal=1 if kind == 1 else 2)
+    below = float(low.abs().max().item())
+    del low
+    tr = torch.diagonal(A, dim1=1, dim2=2).sum(dim=1)
+    trw = w.sum(dim=1)
+    tr_err = float(((tr - (trw if kind == 1 else trw.real)).abs() / (1e-300 + A.abs().amax(dim=(1, 2)) * n)).max().item())
+    invariants = {"max_abs_below_structure": below, "max_rel_trace_minus_sum_w": tr_err}
 
-    # ---- end to end through the public host API (pinned host buffers, H2D + D2H inside the timed region) -------
+    # ---- end to end through the public host API (host buffers, H2D + D2H inside the timed region) -------
     e2e = None
-    if args.e2e_steps > 0:
+    if with_e2e and args.e2e_steps > 0:
+        def run_e2e(Ah_t, Zh_t, steps):
+            Ah_np = Ah_t.numpy().T            # (n, n, batch) Fortran-ordered view of the buffer
+            Zh_np = Zh_t.numpy().T
+            assert Ah_np.flags.f_contiguous
+            times, checksum = [], 0.0
+            for it in range(1 + steps):
+                Ah_t.copy_(A_host)
+                barrier()
+                t0 = time.perf_counter()
+                S = gs.gschur_(Ah_np, Z=Zh_np, devices=[local_rank])
+                checksum = float(np.abs(S.values[:, ::4097]).sum())    # touch the result on the host
+                dt = time.perf_counter() - t0
+                if it > 0:
+                    times.append(dt)
+            e2e_s = float(np.median(times))
+            if world > 1:
+                t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                e2e_s = float(t.item())
+            return e2e_s, times, checksum
+
         Ah = torch.empty((batch, n, n), dtype=tdt).pin_memory()
         Zh = torch.empty((batch, n, n), dtype=tdt).pin_memory()
-        Ah_np = Ah.numpy().T            # (n, n, batch) Fortran-ordered view of the pinned buffer
-        Zh_np = Zh.numpy().T
-        assert Ah_np.flags.f_contiguous
-        times = []
-        for it in range(1 + args.e2e_steps):
-            Ah.copy_(A_host)
-            barrier()
-            t0 = time.perf_counter()
-            S = gs.gschur_(Ah_np, Z=Zh_np, devices=[local_rank])
-            checksum = float(np.abs(S.values[:, ::4097]).sum())    # touch the result on the host
-            dt = time.perf_counter() - t0
-            if it > 0:
-                times.append(dt)
         # median over the steps: single calls are occasionally 2x slower for reasons outside the process (the copies share
         # the host's PCIe root and memory with other tenants of the box); every step's time is reported alongside
-        e2e_s = float(np.median(times))
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+        e2e_s, times, checksum = run_e2e(Ah, Zh, args.e2e_steps)
         h2d = batch * n * n * esz
         d2h = 2 * batch * n * n * esz + batch * n * 16 + batch * 4 + batch * 16
-        e2e = {"value": world * batch / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        e2e = {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps, "stat": "median", "ms_steps": [round(1e3 * t, 1) for t in times],
-               "api": "genericschur_jl_b200.gschur_ (host arrays)",
-               "checksum": checksum}
+               "api": "genericschur_jl_b200.gschur_ (pinned host arrays)", "checksum": checksum}
         del Ah, Zh
+        if with_pageable:
+            # the drop-in caller's arrays are pageable (a Julia Array): same call on ordinary host memory
+            Ap = torch.empty((batch, n, n), dtype=tdt)
+            Zp = torch.empty((batch, n, n), dtype=tdt)
+            try:
+                ps, ptimes, _ = run_e2e(Ap, Zp, max(1, min(2, args.e2e_steps)))
+                e2e["pageable"] = {"value": total / ps, "ms_per_step": 1e3 * ps, "ms_steps": [round(1e3 * t, 1) for t in ptimes]}
+            except Exception as exc:      # informational
+                e2e["pageable"] = {"error": str(exc)}
+            del Ap, Zp
 
-    others = None
-    if rank == 0 and world == 1 and not args.no_others:
-        del A0, A, Z, w, info, stats
-        torch.cuda.empty_cache()
-        others = other_workloads(gs, torch, args.workload)
+    rec = {"workload": name + ": " + desc, "value": value, "unit": UNIT, "ms_per_step": ms_per_step, "steps": args.steps,
+           "warmup": args.warmup, "per_gpu_batch": batch, "total_batch": total, "step_ms": [round(x, 3) for x in step_ms],
+           "invariants_on_timed_output": invariants, "e2e": e2e}
     if rank == 0:
         hbm_peak, hbm_src = measured_peaks()
         fp64_peak, _ = gs.measure_fp64_peak()
-        # Dominant kernel: stage B (gschur_qr_kernel, QR iteration + Z).  Its algorithmic work is the nominal QR share
-        # of SURVEY.md §8d: 69.4 n^3 flops (complex) / 20.3 n^3 (real) per matrix; stage A has the remaining
-        # 18.67 n^3 / 4.67 n^3 (Hessenberg + Q).  Times: CUDA events recorded by the library on the launching stream.
+        # Algorithmic work: QR iteration 69.4 n^3 flops (complex) / 20.3 n^3 (real) per matrix, Hessenberg +
+        # Q the remaining 18.67 n^3 / 4.67 n^3.  The QR work splits between stage B (sweeps on H: n+3 / n+4 row-column pair
+        # updates per reflector) and stage C (the same reflectors on the n rows of Z).
         step_mean = float(np.mean(step_ms))
         qr_flops = (69.4 if kind == 1 else 20.3) * n ** 3
         hq_flops = flops_per_matrix - qr_flops
+        share_b = (n + 3.0) / (2 * n + 3.0) if kind == 1 else (n + 4.0) / (2 * n + 4.0)
+        b_flops, c_flops = qr_flops * share_b, qr_flops * (1.0 - share_b)
+        three = have_stage and ms_c.value > 0
         kernel_ms = float(ms_b.value) if have_stage else step_mean
-        alg_flops = (qr_flops if have_stage else flops_per_matrix) * batch
+        alg_flops = ((b_flops if three else qr_flops) if have_stage else flops_per_matrix) * batch
         alg_bytes = 3 * n * n * esz * batch + n * 16 * batch
         achieved_tf = alg_flops / (kernel_ms * 1e-3) / 1e12
-        # DRAM traffic of the same kernel from the committed ncu capture (profiles/r01f_stageB_cfg3.summary.txt):
-        # 310 MB read + 753 MB written for a 2960-matrix launch = 359 KB per 64x64 c64 matrix (algorithmic: H, Q in and
-        # T, Z out = 262 KB; Z is streamed in place through L2 and dirty lines are written back more than once)
-        ncu_traffic_per_matrix = 359.1e3 if (kind == 1 and n == 64) else None
+        tr = kernel_traffic(kind, n)
         roofline = {
-            "bound": "fp64_fma", "kernel": "gschur_qr_kernel<cx<double>,2> (stage B: QR sweeps + Z)" if kind == 1 else "gschur_qr_kernel (stage B)",
+            "bound": "fp64_fma",
+            "kernel": ("gschur_chain_kernel<T,32,CPL,MINB,1> (stage B: owner-computes QR sweeps on H, reflector log out)" if three
+                       else "gschur_qr_kernel (stage B: QR sweeps + Z)"),
             "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak,
-            "traffic": (ncu_traffic_per_matrix * batch) if ncu_traffic_per_matrix else None,
-            "traffic_note": "dram__bytes_read+write of one ncu --set full capture (2960-matrix launch), scaled per matrix",
+            "traffic": (tr["dram_bytes_per_matrix"] * batch) if tr else None,
+            "traffic_source": tr,
             "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / step_mean,
             "peak_source": "measured live (library DFMA micro-kernel; MEASURED_PEAKS.json has no FP64 figure)",
-            "algorithmic_flops_per_matrix": qr_flops if have_stage else flops_per_matrix,
+            "algorithmic_flops_per_matrix": alg_flops / batch,
             "executed_reflector_applications_per_matrix": executed_units,
             "whole_step": {"achieved": flops_per_matrix * batch / (step_mean * 1e-3) / 1e12,
                            "frac": flops_per_matrix * batch / (step_mean * 1e-3) / 1e12 / fp64_peak,
                            "algorithmic_flops_per_matrix": flops_per_matrix},
-            "stage_a": {"kernel": "gehrd_q_split_kernel (ComplexF64) / gehrd_q_kernel (scale + Hessenberg + Q)", "kernel_ms": float(ms_a.value) if have_stage else None,
+            "stage_a": {"kernel": "gehrd_q_split_kernel (ComplexF64) / gehrd_q_kernel (scale + Hessenberg + Q)",
+                        "kernel_ms": float(ms_a.value) if have_stage else None,
                         "achieved": (hq_flops * batch / (ms_a.value * 1e-3) / 1e12) if have_stage and ms_a.value > 0 else None,
                         "algorithmic_flops_per_matrix": hq_flops},
+            "stage_c": {"kernel": "gschur_zreg_kernel (replay of the reflector log on Z, rows of Z in registers)",
+                        "kernel_ms": float(ms_c.value) if three else None,
+                        "achieved": (c_flops * batch / (ms_c.value * 1e-3) / 1e12) if three else None,
+                        "algorithmic_flops_per_matrix": c_flops if three else None},
+            "qr_total": {"kernel_ms": (float(ms_b.value) + float(ms_c.value)) if have_stage else None,
+                         "achieved": (qr_flops * batch / ((ms_b.value + ms_c.value) * 1e-3) / 1e12) if have_stage else None,
+                         "algorithmic_flops_per_matrix": qr_flops},
             "hbm_view": {"achieved": alg_bytes / (step_mean * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                          "frac": alg_bytes / (step_mean * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                          "algorithmic_bytes_per_matrix": alg_bytes // batch},
         }
-        # L2 view of the same kernel: bytes it moves through L2 per matrix (lts__t_sectors x 32 B of the committed ncu
-        # captures: profiles/r01f_stageB_cfg3.ncu-rep 20.4 MB per 64x64 c64 matrix, r01b_stageB_f64n64.ncu-rep 6.0 MB per
-        # 64x64 f64 matrix — the Z stream) against the L2 streaming bandwidth measured live.
-        roofline["l2_view"] = None
-        l2_per_matrix = {(1, 64): 20.36e6, (0, 64): 6.01e6}.get((kind, n))
-        if l2_per_matrix:
-            try:
-                l2_peak, _ = gs.measure_l2_bandwidth()
-                l2_ach = l2_per_matrix * batch / (kernel_ms * 1e-3) / 1e9
-                roofline["l2_view"] = {"achieved": l2_ach, "peak": l2_peak, "unit": "GB/s", "frac": l2_ach / l2_peak,
-                                       "l2_bytes_per_matrix": l2_per_matrix,
-                                       "peak_source": "measured live (library L2 read-modify-write stream, 38.8 MB resident)"}
-            except Exception as exc:   # the probe is informational: never lose the bench line over it
-                roofline["l2_view"] = {"error": str(exc)}
+        if roofline["qr_total"]["achieved"]:
+            roofline["qr_total"]["frac"] = roofline["qr_total"]["achieved"] / fp64_peak
+        rec["roofline"] = roofline
+    del A0, A, Z, w, info, stats
+    torch.cuda.empty_cache()
+    return rec, clocks, launches, t_wall
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the per-GPU batch is fixed (65536 each); strong: BASELINE config 3 as stated — 65536 matrices in "
+                         "total, split over the ranks")
+    ap.add_argument("--batch", type=int, default=0, help="override the (per-GPU / total) batch (development only)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the runs of the other BASELINE configs")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    gs = load_package()
+    kind, n, batch, flops_per_matrix, desc = WORKLOADS[args.workload]
+    if args.batch:
+        batch = args.batch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = max(world, 1)     # a bare `python bench.py --gpus N` without torchrun runs as one rank
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the Schur path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    rec, clocks, launches, t_wall = measure_workload(gs, torch, dist, args, args.workload, world, rank, local_rank,
+                                                     with_e2e=True, with_pageable=(world == 1))
+    esz = 16 if kind == 1 else 8
+    # BASELINE's metric text names the Float64 n = 64 batch: measured the same way (same steps / warm-up, CUDA events, e2e)
+    f64rec = None
+    if args.workload != "f64n64" and not args.no_others:
+        f64rec, _, _, _ = measure_workload(gs, torch, dist, args, "f64n64", world, rank, local_rank, with_e2e=True)
+    others = None
+    if rank == 0 and world == 1 and not args.no_others:
+        others = other_workloads(gs, torch, args.workload)
+    if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
             cpu, _, _ = cpu_baseline(kind, n, batch, 1234 + 3)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": rec["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload + ": " + desc, "n": n,
-                       "element": "ComplexF64" if kind == 1 else "Float64", "per_gpu_batch": batch,
-                       "l2_policy": "inputs_exceed_l2" if batch * n * n * esz > 2 * 126e6 else "inputs_fit_l2",
+            "config": {"workload": rec["workload"], "n": n,
+                       "element": "ComplexF64" if kind == 1 else "Float64", "per_gpu_batch": rec["per_gpu_batch"],
+                       "total_batch": rec["total_batch"],
+                       "l2_policy": "inputs_exceed_l2" if rec["per_gpu_batch"] * n * n * esz > 2 * 126e6 else "inputs_fit_l2",
                        "sharding": "independent per-GPU shards, no collective"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "wall_s_timed_region": t_wall, "other_workloads": others,
+            "clocks": clocks, "e2e": rec["e2e"], "gpu_launches": int(launches), "roofline": rec.get("roofline"),
+            "cpu_baseline": cpu, "wall_s_timed_region": t_wall,
+            "invariants_on_timed_output": rec["invariants_on_timed_output"],
+            "f64n64": f64rec, "other_workloads": others,
         }
         print(json.dumps(line))
     if world > 1:

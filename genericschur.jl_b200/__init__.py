@@ -31,7 +31,7 @@ from ._lib import C64, CDD, DD, F64
 __all__ = [
     "gschur", "gschur_", "gschur_batched_", "schur", "schur_", "eigvals", "eigvals_", "hessenberg", "hessenberg_",
     "gschur_hess_", "gschur_device_", "Schur", "Hessenberg", "UnconvergedException", "DimensionMismatch",
-    "ArgumentError", "DDArray", "CDDArray", "F64", "C64", "DD", "CDD", "device_count", "launch_count",
+    "ArgumentError", "DDArray", "CDDArray", "F64", "C64", "DD", "CDD", "device_count", "launch_count", "release_workspace",
 ]
 
 
@@ -312,6 +312,14 @@ def hessenberg_(A, wantQ=True, devices=None):
         raise ArgumentError("A must be a writeable Fortran-ordered (column-major) array")
     nb = 1 if batch is None else batch
     tshape = A.shape[:lead] + (max(n - 1, 0),) + (() if batch is None else (batch,))
+    if kind == F64 and batch is None and n > max_batched_n(F64):
+        # one large Float64 matrix: the blocked WY reduction of regime 2 (csrc/large_gehrd.cuh)
+        tau = np.zeros(n - 1, dtype=np.float64)
+        Q = np.zeros_like(A) if wantQ else None
+        rc = _lib.lib().gschur_cuda_hessenberg_large(n, _ptr(A), n, _ptr(tau), _ptr(Q), n, 0)
+        if rc != 0:
+            raise RuntimeError(f"libgschur_cuda error {rc}: {_lib.lib().gschur_cuda_large_last_error().decode()}")
+        return Hessenberg(A, tau, Q)
     tau = np.zeros(tshape, dtype=A.dtype, order="F")
     if isinstance(A, (DDArray, CDDArray)):
         tau = tau.view(type(A))
@@ -343,6 +351,11 @@ def gschur_hess_(H, Z=None, maxiter=None, checksd=True):
             raise DimensionMismatch("second dimension of Z must match H")
     flags = _lib.FLAG_HESS_INPUT | (_lib.FLAG_CHECK_SUBDIAG if checksd else 0)
     return gschur_(H, wantZ=Z is not None, scale=False, maxiter=maxiter, flags=flags, Z=Z)
+
+
+def release_workspace():
+    """Free the device / pinned buffers the library caches between calls (gschur_cuda_release_workspace)."""
+    return _lib.lib().gschur_cuda_release_workspace()
 
 
 def gschur_device_(kind, n, batch, A_ptr, Z_ptr, w_ptr, info_ptr=None, stats_ptr=None, scale=True, maxiter=0,

@@ -30,6 +30,7 @@ EXPORTS = [
     "gschur_cuda_measure_l2_bandwidth",
     "gschur_cuda_stage_timing",
     "gschur_cuda_stage_timing3",
+    "gschur_cuda_release_workspace",
     "gschur_cuda_hessenberg_large",
     "gschur_cuda_large",
     "gschur_cuda_dgemm",

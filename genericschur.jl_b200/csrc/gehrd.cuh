@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(NT) gehrd_q_kernel(BatchedParams p) {
         T* gZ = wantZ ? reinterpret_cast<T*>(p.Z) + b * p.strideZ : nullptr;
         if (GT) {
             // tile = this matrix's Z buffer (or its slice of the scratch tile array when Z is not wanted)
-            H = wantZ ? gZ : reinterpret_cast<T*>(p.tau) + (size_t)blockIdx.x * n * n;
+            H = wantZ ? gZ : reinterpret_cast<T*>(p.gt_tiles) + (size_t)blockIdx.x * n * n;
             S.H = H;
         }
 
@@ -99,10 +99,16 @@ __global__ void __launch_bounds__(NT) gehrd_q_kernel(BatchedParams p) {
         R cscale = r_const<R>(1.0), anrm = r_const<R>(1.0);
         if (p.scale) scaled = S.scale_in(cscale, anrm);
         S.hessenberg();
-        // ---- H out (upper Hessenberg part, zeros below) ----
+        // ---- H out: the upper Hessenberg part with zeros below it (Schur requests), or the factored form — H above, the
+        //      reflector tails below the sub-diagonal, tau separately — that hessenberg! returns (src/hessenberg.jl:3-17) ----
+        const bool factors = p.mode == MODE_HESSENBERG;
         for (int e = tid; e < n * n; e += NT) {
             int i = e % n, j = e / n;
-            gA[i + (size_t)j * p.lda] = (i <= j + 1) ? H[i + (size_t)j * ld] : e_zero<T>();
+            gA[i + (size_t)j * p.lda] = (factors || i <= j + 1) ? H[i + (size_t)j * ld] : e_zero<T>();
+        }
+        if (factors && p.tau) {
+            T* gtau = reinterpret_cast<T*>(p.tau) + b * (long long)(n > 1 ? n - 1 : 0);
+            for (int e = tid; e < n - 1; e += NT) gtau[e] = S.sTau[e];
         }
         if (tid == 0 && p.scratch) {
             double* sc = p.scratch + 8 * b;
@@ -186,7 +192,7 @@ template <class T, int NT, bool GT> int launch_gehrd_v(const BatchedParams& p, i
             *err = std::string("cudaMallocAsync(tiles): ") + cudaGetErrorString(e);
             return -2;
         }
-        q.tau = tiles;
+        q.gt_tiles = tiles;
     }
     kern<<<(unsigned)grid, NT, smem, stream>>>(q);
     note_launch();

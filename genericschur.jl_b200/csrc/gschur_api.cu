@@ -4,6 +4,7 @@
 //    thread per device, no collective), each slice is pipelined in chunks over three streams so that
 //    H2D, compute and D2H overlap.
 // There is no CPU fallback anywhere in this file.
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -120,9 +121,13 @@ int check_args(int kind, int n, int64_t batch, const void* A, int lda, int64_t s
         if (batch > 1 && strideZ < (int64_t)ldz * (n - 1) + n) return fail(GSCHUR_ERR_ARG, "strideZ overlaps matrices");
     }
     if (!w) return fail(GSCHUR_ERR_ARG, "w is NULL");
-    if (n > (schur_mode ? max_schur_n(kind) : max_batched_n(kind)))
-        return fail(GSCHUR_ERR_SIZE, "n = " + std::to_string(n) + " exceeds the batched-kernel limit " +
-                                         std::to_string(max_batched_n(kind)) + " for this kind");
+    // Schur and Hessenberg-only requests share the stage A kernel and therefore the limit; the single-kernel path that
+    // GSCHUR_FORCE_GENERIC selects holds the whole problem in shared memory and takes less
+    (void)schur_mode;
+    const int lim = std::getenv("GSCHUR_FORCE_GENERIC") ? std::min(max_schur_n(kind), max_batched_n(kind)) : max_schur_n(kind);
+    if (n > lim)
+        return fail(GSCHUR_ERR_SIZE, "n = " + std::to_string(n) + " exceeds the batched-kernel limit " + std::to_string(lim) +
+                                         " for this kind");
     return 0;
 }
 
@@ -239,6 +244,26 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
     if (chunk < min_chunk) chunk = min_chunk;
     if (chunk > count) chunk = count;
     const bool wantZ = J.Z != nullptr;
+    {
+        // Device-memory budget of the NBUF chunk buffers (A and Z per matrix): GSCHUR_PIPE_BUDGET_MB (default 8 GiB),
+        // never more than a quarter of what is free now — the kernels' own workspaces (reflector log pool) need room
+        // too.  A larger slice simply flows through more chunks.
+        size_t budget = (size_t)8 << 30;
+        if (const char* e = std::getenv("GSCHUR_PIPE_BUDGET_MB")) {
+            const long long v = std::atoll(e);
+            if (v >= 1) budget = (size_t)v << 20;
+        }
+        if (cudaSetDevice(dev) == cudaSuccess) {
+            size_t fr = 0, tot = 0;
+            size_t have = 0;
+            for (int i = 0; i < NBUF; ++i) have += g_pipe[dev].buf[i].capA + g_pipe[dev].buf[i].capZ;
+            if (cudaMemGetInfo(&fr, &tot) == cudaSuccess && (fr + have) / 4 < budget) budget = (fr + have) / 4;
+        }
+        const size_t per_matrix = (size_t)NBUF * (wantZ ? 2 : 1) * mat + 64 * NBUF;
+        int64_t fit = (int64_t)(budget / per_matrix);
+        if (fit < 1) fit = 1;
+        if (chunk > fit) chunk = fit;
+    }
     const bool hess = J.mode == MODE_HESSENBERG;
     const bool zin = wantZ && (J.flags & GSCHUR_FLAG_HESS_INPUT) && !hess;
     const bool denseA = (J.lda == n) && (J.strideA == (int64_t)n * n);
@@ -274,6 +299,33 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
         P.hcap = stage_bytes;
     }
     char* hst = P.hstage;
+    // Pageable caller memory (a Julia Array, an ordinary numpy array): cudaMemcpyAsync from / to it is staged by the driver
+    // and synchronous with respect to the host, which serialises the three-stream pipeline.  The slice's ranges of A and Z
+    // are therefore page-locked for the duration of the call (GSCHUR_HOST_REGISTER=0 turns this off); memory that is
+    // already pinned or registered is left alone.
+    void* reg_ptr[2] = {nullptr, nullptr};
+    {
+        const char* hr = std::getenv("GSCHUR_HOST_REGISTER");
+        const bool want_reg = !(hr && hr[0] == '0');
+        auto try_register = [&](char* base, bool dense, int64_t stride, int ld, int slot) {
+            if (!want_reg || !base || !dense) return;
+            (void)stride;
+            (void)ld;
+            char* lo = base + (size_t)b0 * mat;
+            const size_t bytes = (size_t)count * mat;
+            if (bytes < ((size_t)32 << 20)) return;     // small slices: the registration costs more than it saves
+            cudaPointerAttributes at;
+            if (cudaPointerGetAttributes(&at, lo) != cudaSuccess) {
+                cudaGetLastError();
+                return;
+            }
+            if (at.type != cudaMemoryTypeUnregistered) return;
+            if (cudaHostRegister(lo, bytes, cudaHostRegisterDefault) == cudaSuccess) reg_ptr[slot] = lo;
+            else cudaGetLastError();
+        };
+        try_register(J.A, denseA, J.strideA, J.lda, 0);
+        try_register(J.Z, wantZ && denseZ, J.strideZ, J.ldz, 1);
+    }
     if (!P.sH2D) SL_TRY(cudaStreamCreateWithFlags(&P.sH2D, cudaStreamNonBlocking));
     if (!P.sComp) SL_TRY(cudaStreamCreateWithFlags(&P.sComp, cudaStreamNonBlocking));
     if (!P.sD2H) SL_TRY(cudaStreamCreateWithFlags(&P.sD2H, cudaStreamNonBlocking));
@@ -295,7 +347,7 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
         std::vector<int64_t> sizes;
         {
             int64_t left = count;
-            const bool taper = count >= 4 * chunk && chunk >= 4 * min_chunk;
+            const bool taper = count >= 4 * chunk && chunk >= 4 * min_chunk && count <= 64 * chunk;
             if (taper) {
                 sizes.push_back(chunk / 4);
                 sizes.push_back(chunk / 2);
@@ -410,6 +462,8 @@ cleanup:
         cudaEventDestroy(tevK1);
         cudaEventDestroy(tevD1);
     }
+    for (int i = 0; i < 2; ++i)
+        if (reg_ptr[i]) cudaHostUnregister(reg_ptr[i]);
     if (rc_final == 0) {
         if (!hess) std::memcpy(J.w + (size_t)b0 * n * ws, hst + off_w, ws * n * (size_t)count);
         if (hess && n > 1) std::memcpy(J.tau + (size_t)b0 * tau_per, hst + off_w, tau_per * (size_t)count);
@@ -505,6 +559,45 @@ int gschur_cuda_stage_timing(int enable, float* ms_stage_a, float* ms_stage_b) {
     return rc;
 }
 
+int gschur_cuda_release_workspace(void) {
+    // frees what the host-pointer pipeline caches per device (chunk buffers, pinned staging) and returns the
+    // stream-ordered allocations of the batched paths (scale info, reflector log pools) to the driver
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess) return GSCHUR_ERR_CUDA;
+    int prev = 0;
+    cudaGetDevice(&prev);
+    for (int d = 0; d < have && d < kMaxDevices; ++d) {
+        DevicePipe& P = g_pipe[d];
+        std::lock_guard<std::mutex> lk(P.mu);
+        bool any = P.hstage != nullptr;
+        for (int i = 0; i < NBUF; ++i) any = any || P.buf[i].dA || P.buf[i].dZ || P.buf[i].dw || P.buf[i].dtau || P.buf[i].dinfo || P.buf[i].dstats;
+        if (cudaSetDevice(d) != cudaSuccess) continue;
+        if (any) {
+            cudaDeviceSynchronize();
+            for (int i = 0; i < NBUF; ++i) {
+                ChunkBuf& B = P.buf[i];
+                if (B.dA) cudaFree(B.dA);
+                if (B.dZ) cudaFree(B.dZ);
+                if (B.dw) cudaFree(B.dw);
+                if (B.dtau) cudaFree(B.dtau);
+                if (B.dinfo) cudaFree(B.dinfo);
+                if (B.dstats) cudaFree(B.dstats);
+                B.dA = B.dZ = B.dw = B.dtau = nullptr;
+                B.dinfo = nullptr;
+                B.dstats = nullptr;
+                B.capA = B.capZ = B.capw = B.captau = B.capn = B.capst = 0;
+            }
+            if (P.hstage) cudaFreeHost(P.hstage);
+            P.hstage = nullptr;
+            P.hcap = 0;
+        }
+        cudaMemPool_t mp = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&mp, d) == cudaSuccess && mp) cudaMemPoolTrimTo(mp, 0);
+    }
+    cudaSetDevice(prev);
+    return 0;
+}
+
 int gschur_cuda_max_batched_n(int kind) {
     if (kind < 0 || kind > 3) return 0;
     return max_schur_n(kind);
@@ -530,13 +623,18 @@ int gschur_cuda_batched(int kind, int n, int64_t batch, void* A, int lda, int64_
     if (n == 0 || batch == 0) return 0;
     if (gschur_cuda_device_count() < 1) return fail(GSCHUR_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
     if (flags & GSCHUR_FLAG_DEVICE_PTRS) {
+        // the return value counts failures even when the caller does not want the per-matrix codes
+        int32_t* dinfo = info;
+        if (!dinfo) CUDA_TRY(cudaMalloc((void**)&dinfo, sizeof(int32_t) * (size_t)batch));
         rc = enqueue_device(kind, MODE_SCHUR, n, batch, A, lda, strideA, Z, ldz, strideZ, w, nullptr, scale, maxiter,
-                            info, stats, (cudaStream_t)0, flags);
-        if (rc) return rc;
-        CUDA_TRY(cudaStreamSynchronize((cudaStream_t)0));
-        if (!info) return 0;
+                            dinfo, stats, (cudaStream_t)0, flags);
         std::vector<int32_t> h((size_t)batch);
-        CUDA_TRY(cudaMemcpy(h.data(), info, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost));
+        cudaError_t ce = cudaSuccess;
+        if (!rc) ce = cudaStreamSynchronize((cudaStream_t)0);
+        if (!rc && ce == cudaSuccess) ce = cudaMemcpy(h.data(), dinfo, sizeof(int32_t) * batch, cudaMemcpyDeviceToHost);
+        if (!info) cudaFree(dinfo);
+        if (rc) return rc;
+        CUDA_TRY(ce);
         int64_t bad = 0;
         for (int64_t b = 0; b < batch; ++b) {
             if (h[b] == GSCHUR_ERR_SUBDIAG) return fail(GSCHUR_ERR_SUBDIAG, "ArgumentError: algorithm assumes real subdiagonal");

@@ -10,6 +10,7 @@ struct BatchedParams {
     void* Z;      // nullptr: wantZ = false
     void* w;      // complex eigenvalues, n per matrix
     void* tau;    // hessenberg-only mode: (n-1) per matrix
+    void* gt_tiles;   // stage A, global-tile variant without a Z buffer: one n x n scratch tile per resident CTA
     long long strideA, strideZ, batch;
     int lda, ldz, n;
     int scale, maxiter;

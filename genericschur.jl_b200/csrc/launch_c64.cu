@@ -1,7 +1,8 @@
 // Kernel instantiations for element kind c64 (one translation unit per kind keeps builds parallel).
 // Schur requests go to the three-stage path (qr3.cuh, n <= 64; GSCHUR_QR=fused forces the fused stage B) or the
-// two-kernel path (gehrd.cuh + fastqr.cuh, n <= 128); Hessenberg-only requests and
-// anything forced by GSCHUR_FORCE_GENERIC to the block-synchronous single-kernel path (batched.cuh).
+// two-kernel path (gehrd.cuh + fastqr.cuh, n <= 128); Hessenberg-only requests to the
+// stage A kernel (gehrd.cuh, factor output); anything forced by GSCHUR_FORCE_GENERIC to the block-synchronous
+// single-kernel path (batched.cuh).
 #include <cstdlib>
 #include "qr3.cuh"
 namespace gs {
@@ -18,6 +19,8 @@ int launch_c64(const BatchedParams& p, int dev_sms, cudaStream_t stream, std::st
         if (p.n <= 96) return launch_fast<cx<double>, 3>(p, dev_sms, stream, err);
         if (p.n <= 128) return launch_fast<cx<double>, 4>(p, dev_sms, stream, err);
     }
+    // Hessenberg-only requests: the stage A kernel in its factor-output mode (same size limits as the Schur path)
+    if (!force_generic && p.mode == MODE_HESSENBERG) return launch_gehrd<cx<double>, 64>(p, dev_sms, stream, err);
     return launch_t<cx<double>>(p, dev_sms, stream, err);
 }
 }  // namespace gs

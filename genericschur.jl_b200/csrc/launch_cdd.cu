@@ -1,6 +1,7 @@
 // Kernel instantiations for element kind cdd (one translation unit per kind keeps builds parallel).
-// Schur requests go to the two-kernel path (gehrd.cuh + fastqr.cuh, n <= 96); Hessenberg-only requests and
-// anything forced by GSCHUR_FORCE_GENERIC to the block-synchronous single-kernel path (batched.cuh).
+// Schur requests go to the two-kernel path (gehrd.cuh + fastqr.cuh, n <= 96); Hessenberg-only requests to the
+// stage A kernel (gehrd.cuh, factor output); anything forced by GSCHUR_FORCE_GENERIC to the block-synchronous
+// single-kernel path (batched.cuh).
 #include <cstdlib>
 #include "fastqr.cuh"
 namespace gs {
@@ -11,6 +12,8 @@ int launch_cdd(const BatchedParams& p, int dev_sms, cudaStream_t stream, std::st
         if (p.n <= 64) return launch_fast<cx<dd_t>, 2>(p, dev_sms, stream, err);
         if (p.n <= 96) return launch_fast<cx<dd_t>, 3>(p, dev_sms, stream, err);
     }
+    // Hessenberg-only requests: the stage A kernel in its factor-output mode (same size limits as the Schur path)
+    if (!force_generic && p.mode == MODE_HESSENBERG) return launch_gehrd<cx<dd_t>, 64>(p, dev_sms, stream, err);
     return launch_t<cx<dd_t>>(p, dev_sms, stream, err);
 }
 }  // namespace gs

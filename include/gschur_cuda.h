@@ -122,6 +122,13 @@ int gschur_cuda_stage_timing(int enable, float* ms_stage_a, float* ms_stage_b);
 int gschur_cuda_stage_timing3(int enable, float* ms_stage_a, float* ms_stage_b, float* ms_stage_c);
 
 /*
+ * Frees everything the library caches between calls: the per-device chunk buffers and pinned staging block of the
+ * host-pointer pipeline, and the stream-ordered workspace pool of the batched kernels (scale records, reflector log).
+ * The next call allocates again.  Returns 0.
+ */
+int gschur_cuda_release_workspace(void);
+
+/*
  * Batched Householder reduction to Hessenberg form, A_b = Q_b H_b Q_b^H.
  * Replaces _hessenberg!(A) src/hessenberg.jl:3-17 (LinearAlgebra.hessenberg! src/pirates.jl:232) and
  * _materializeQ(H) src/hessenberg.jl:150-166.

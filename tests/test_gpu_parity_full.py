@@ -289,3 +289,63 @@ def test_cfg4_parity(gs, O):
     # both solvers are backward stable to n ulp ||A||_2 ~ 1e-9 here; eigenvalue condition numbers of a random matrix of
     # this size reach O(1e2)
     assert dist.max() < 1e-6, float(dist.max())
+
+
+def test_hessenberg_shares_the_schur_limits(gs, O):
+    """Hessenberg-only requests run on the stage A kernel: the same size limits as gschur! (128 for the Float64 kinds, 96
+    for the double-double kinds), factors and tau as hessenberg! returns them (src/hessenberg.jl:3-17)."""
+    rng = np.random.default_rng(41)
+    for kind, n in ((0, 128), (1, 100), (1, 128)):
+        A = np.asfortranarray(rng.random((n, n, 2)) + (1j * rng.random((n, n, 2)) if kind else 0))
+        Hs = gs.hessenberg(A)
+        for b in range(2):
+            F = Hs.factors[:, :, b]
+            berr, oerr, _ = O.residuals(A[:, :, b], np.triu(F, -1), Hs.Q[:, :, b], kind)
+            assert berr < 10 and oerr < 10, (kind, n, berr, oerr)
+            Fo, tauo, _ = O.hessenberg(A[:, :, b], kind)
+            np.testing.assert_allclose(np.triu(F, -1), np.triu(Fo, -1), rtol=0, atol=1e-10 * np.abs(A).max())
+            np.testing.assert_allclose(np.tril(F, -2), np.tril(Fo, -2), rtol=0, atol=1e-10)
+            np.testing.assert_allclose(Hs.tau[:, b], tauo, rtol=0, atol=1e-11)
+    # one large Float64 matrix goes to the blocked reduction
+    n = 300
+    A = np.asfortranarray(rng.random((n, n)))
+    Hs = gs.hessenberg(A)
+    Hm = np.triu(Hs.factors, -1)
+    assert np.linalg.norm(A - Hs.Q @ Hm @ Hs.Q.T) / (n * ULP * np.linalg.norm(A)) < 10
+    assert np.linalg.norm(Hs.Q.T @ Hs.Q - np.eye(n)) / (n * ULP) < 10
+
+
+def test_device_mode_counts_failures_without_info(gs):
+    """GSCHUR_FLAG_DEVICE_PTRS with info == NULL: the return value still counts the matrices that hit the iteration cap."""
+    import ctypes
+    import torch
+    from genericschur_jl_b200 import _lib
+    L = _lib.lib()
+    n, batch = 6, 5
+    A = torch.rand((batch, n, n), dtype=torch.float64, device="cuda")
+    A[1, 2, 3] = float("nan")
+    A[3, 0, 0] = float("nan")
+    Z = torch.empty_like(A)
+    w = torch.empty((batch, n), dtype=torch.complex128, device="cuda")
+    rc = L.gschur_cuda_batched(0, n, batch, ctypes.c_void_p(A.data_ptr()), n, n * n, ctypes.c_void_p(Z.data_ptr()), n,
+                               n * n, ctypes.c_void_p(w.data_ptr()), 1, 0, None, None, None, 0, _lib.FLAG_DEVICE_PTRS)
+    assert rc == 2, rc
+
+
+def test_pipeline_budget_and_release(gs, O, monkeypatch):
+    """The host-pointer pipeline bounds its device buffers by a byte budget (more, smaller chunks: same result bit for bit)
+    and gschur_cuda_release_workspace() frees what is cached; pageable and pinned callers get the same result."""
+    rng = np.random.default_rng(43)
+    n, batch = 24, 6000
+    A = np.asfortranarray(rng.random((n, n, batch)))
+    S0 = gs.gschur(A)
+    monkeypatch.setenv("GSCHUR_PIPE_BUDGET_MB", "1")       # 1 MiB: ~56 matrices per chunk
+    S1 = gs.gschur(A)
+    monkeypatch.delenv("GSCHUR_PIPE_BUDGET_MB")
+    assert np.array_equal(S0.T, S1.T) and np.array_equal(S0.Z, S1.Z) and np.array_equal(S0.values, S1.values)
+    assert gs.release_workspace() == 0
+    monkeypatch.setenv("GSCHUR_HOST_REGISTER", "0")
+    S2 = gs.gschur(A)
+    assert np.array_equal(S0.T, S2.T) and np.array_equal(S0.Z, S2.Z)
+    for b in (0, batch - 1):
+        _check_one(O, A[:, :, b], S1.T[:, :, b], S1.Z[:, :, b], S1.values[:, b], 0, 10, f"budget[{b}]")
