@@ -300,13 +300,15 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
     }
     char* hst = P.hstage;
     // Pageable caller memory (a Julia Array, an ordinary numpy array): cudaMemcpyAsync from / to it is staged by the driver
-    // and synchronous with respect to the host, which serialises the three-stream pipeline.  The slice's ranges of A and Z
-    // are therefore page-locked for the duration of the call (GSCHUR_HOST_REGISTER=0 turns this off); memory that is
-    // already pinned or registered is left alone.
+    // and synchronous with respect to the host, which serialises the three-stream pipeline.  GSCHUR_HOST_REGISTER=1
+    // page-locks the slice's ranges of A and Z for the duration of the call; memory that is already pinned or registered
+    // is left alone.  Off by default: measured on the B200 boxes (65536 x 64x64 ComplexF64, fresh arrays) page-locking
+    // 8.6 GB costs as much as it saves (1.65 s against 1.45-1.63 s without; 0.36 s from pinned arrays) — a caller that
+    // reuses its arrays should pin them once itself.
     void* reg_ptr[2] = {nullptr, nullptr};
     {
         const char* hr = std::getenv("GSCHUR_HOST_REGISTER");
-        const bool want_reg = !(hr && hr[0] == '0');
+        const bool want_reg = hr && hr[0] == '1';
         auto try_register = [&](char* base, bool dense, int64_t stride, int ld, int slot) {
             if (!want_reg || !base || !dense) return;
             (void)stride;

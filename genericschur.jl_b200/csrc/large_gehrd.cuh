@@ -8,6 +8,7 @@
 //   per panel: the right and left block-reflector updates and Y's top rows as FP64 DMMA GEMMs (dgemm.cuh).
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <math.h>
 #include <string>
 #include "dgemm.cuh"
@@ -15,7 +16,7 @@
 namespace gs {
 
 constexpr int LG_NB = 32;          // panel width
-constexpr int LG_PT = 512;         // threads of the single-CTA panel kernel (128 registers each: 32 running sums)
+constexpr int LG_PT = 512;         // threads of the single-CTA panel finish kernel
 constexpr int LG_GEMV_ROWS = 512;  // rows per gemv CTA (two rows per thread, 128-bit loads: 4 KB contiguous per column and CTA)
 constexpr int LG_MAXCHUNKS = 64;   // column chunks of the panel gemv (partial sums are reduced by the next panel kernel)
 
@@ -46,118 +47,207 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// Single CTA.  Panel starts at column p (0-based), local column i (1-based, 1..ib): global column c = p + i - 1.
+// The panel column kernel.  ONE thread-block cluster of LG_NC CTAs (distributed shared memory): the m rows of the
+// panel's V / Y blocks are split over the CTAs of the cluster, every CTA keeps its rows of the column in its own shared
+// memory, and the full-column reductions (V'b, the norm, V'v) are exchanged through DSMEM — every CTA publishes its
+// partial sums in its own shared memory, cluster.sync(), every CTA adds up the partials of all ranks.  (Round 1 ran this
+// on a single CTA: 82 us per column against 23 us for the gemv that streams the trailing matrix.)
+// Panel starts at column p (0-based), local column i (1-based, 1..ib): global column c = p + i - 1.
 // Rows of the panel's V / Y blocks: r0 = p + 1 .. n-1 (index rr = row - r0).
-__global__ void __launch_bounds__(LG_PT) lg_panel_col_kernel(LargeWork w, int p, int i) {
+constexpr int LG_NC = 16;          // CTAs per cluster (non-portable size, allowed on sm_100)
+constexpr int LG_CT = 256;         // threads per CTA of the panel kernel
+
+__device__ __forceinline__ void lg_block_sum32(double (&part)[LG_NB], int nv, double* red, double* out, int tid) {
+    // sums part[q] (q < nv) over the CTA; result in out[q] (shared), valid after the trailing __syncthreads
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int q = 0; q < LG_NB; ++q) {
+        if (q < nv) {
+            const double s = warp_sum(part[q]);
+            if (lane == 0) red[warp * 32 + q] = s;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double s = 0.0;
+        if (lane < nv)
+            for (int ww = 0; ww < LG_CT / 32; ++ww) s += red[ww * 32 + lane];
+        if (lane < LG_NB) out[lane] = (lane < nv) ? s : 0.0;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(LG_CT) lg_panel_col_kernel(LargeWork w, int p, int i) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
     extern __shared__ double sm[];
     const int n = w.n, r0 = p + 1, m = n - r0;       // m rows in the block
     const int c = p + i - 1;
-    double* b = sm;                                   // m doubles: the column being reduced
-    double* red = sm + ((m + 31) & ~31);              // 32 x 32 reduction scratch
-    double* wv = red + 32 * 32;                       // nb: small vectors
+    const int rpc = (((m + LG_NC - 1) / LG_NC) + 31) & ~31;     // rows per CTA
+    const int lo = rank * rpc, hi = min(m, lo + rpc);            // this CTA's rows [lo, hi)
+    double* b = sm;                                   // rpc doubles: this CTA's rows of the column being reduced
+    double* red = sm + rpc;                           // (LG_CT / 32) x 32 reduction scratch
+    double* xch = red + (LG_CT / 32) * 32;            // 40 doubles published to the cluster: [0..31] sums, [32] amax / ssq, [33] alpha
+    double* wv = xch + 40;                            // nb: small vectors
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nbv = i - 1;                            // number of previous reflectors in this panel
     double* Tp = w.T + (size_t)(p / w.nb) * w.nb * w.nb;
     double* Vp = w.V + (size_t)r0 + (size_t)p * n;    // V block: Vp[rr + j*n]
     double* Yp = w.Y + r0;                            // Y block rows r0..: Yp[rr + j*n]
-
-    // (0) finish Y(:, i-1) and T(:, i-1) from the previous column's gemv partial sums
-    if (nbv >= 1) {
-        const int j = nbv - 1;                        // 0-based index of the previous reflector
-        const double tauj = w.tsave[w.nb];
-        for (int rr = tid; rr < m; rr += LG_PT) {
-            double y = w.ypart[r0 + rr];          // accumulated by the gemv CTAs with atomicAdd
-            w.ypart[r0 + rr] = 0.0;               // ready for the next gemv
-            for (int q = 0; q < j; ++q) y -= Yp[rr + (size_t)q * n] * w.tsave[q];
-            Yp[rr + (size_t)j * n] = tauj * y;
-        }
+    double* bc = wv + 3 * LG_NB;                      // 4 doubles: cluster-wide scalars broadcast to the CTA
+    // Cluster-wide sums of the published values (call after cluster.sync()).  The remote reads are spread over the lanes
+    // (one DSMEM round trip instead of LG_NC dependent ones).
+    auto gather_vec = [&]() {                         // returns, in warp 0 lane q, the sum over the ranks of xch[q]
+        static_assert(LG_NC == 2 * (LG_CT / 32), "two ranks per warp");
+        red[warp * 32 + lane] = cluster.map_shared_rank(xch, warp)[lane] + cluster.map_shared_rank(xch, warp + LG_CT / 32)[lane];
+        __syncthreads();
+        double sres = 0.0;
+        if (warp == 0)
+            for (int ww = 0; ww < LG_CT / 32; ++ww) sres += red[ww * 32 + lane];
+        __syncthreads();
+        return sres;
+    };
+    auto gather_scalars = [&](bool want_max) {        // bc[0] = max or sum over the ranks of xch[32], bc[1] = sum of xch[33]
         if (warp == 0) {
+            double a = 0.0, s1 = 0.0;
+            if (lane < LG_NC) {
+                const double* x = cluster.map_shared_rank(xch, lane);
+                a = x[32];
+                s1 = x[33];
+            }
+            a = want_max ? warp_max(a) : warp_sum(a);
+            s1 = warp_sum(s1);
+            if (lane == 0) {
+                bc[0] = a;
+                bc[1] = s1;
+            }
+        }
+        __syncthreads();
+    };
+
+    // (0) + (1) in one pass over the rows: finish Y(:, i-1) (and, rank 0, T(:, i-1)) from the previous column's gemv
+    //     sums; load the column and apply the right-update of the previous reflectors,
+    //     b = A(:, c) - Y(:, 0:nbv-1) * V(i-2, 0:nbv-1)'.  All loads of a row are issued together (one L2 round trip).
+    double* ts = wv + LG_NB;                          // tsave (V2' v of the previous column) and the row V(c, 0:nbv-1)
+    double* vr = ts + LG_NB;
+    if (tid < LG_NB) {
+        ts[tid] = (tid < nbv) ? w.tsave[tid] : 0.0;
+        vr[tid] = (tid < nbv) ? Vp[(nbv - 1) + (size_t)tid * n] : 0.0;
+    }
+    __syncthreads();
+    {
+        const int j = nbv - 1;                        // 0-based index of the previous reflector (if any)
+        const double tauj = (nbv >= 1) ? w.tsave[w.nb] : 0.0;
+        for (int rr = lo + tid; rr < hi; rr += LG_CT) {
+            double yrow[LG_NB];
+#pragma unroll
+            for (int q = 0; q < LG_NB; ++q) yrow[q] = (q < j) ? Yp[rr + (size_t)q * n] : 0.0;
+            double v = w.A[(size_t)(r0 + rr) + (size_t)c * n];
+            if (nbv >= 1) {
+                double y = w.ypart[r0 + rr];          // accumulated by the gemv CTAs with atomicAdd
+                w.ypart[r0 + rr] = 0.0;               // ready for the next gemv
+#pragma unroll
+                for (int q = 0; q < LG_NB; ++q) y -= yrow[q] * ts[q];      // ts[q] = 0 for q >= j: yrow is 0 there anyway
+                y *= tauj;
+                Yp[rr + (size_t)j * n] = y;
+                v -= y * vr[j];
+            }
+#pragma unroll
+            for (int q = 0; q < LG_NB; ++q) v -= yrow[q] * vr[q];
+            b[rr - lo] = v;
+        }
+        if (nbv >= 1 && rank == 0 && warp == 0) {
             // T(0:j-1, j) = -tau * T(0:j-1, 0:j-1) * tsave ;  T(j, j) = tau
             double acc = 0.0;
             if (lane < j)
-                for (int q = lane; q < j; ++q) acc += Tp[lane + q * w.nb] * w.tsave[q];
+                for (int q = lane; q < j; ++q) acc += Tp[lane + q * w.nb] * ts[q];
             if (lane < j) Tp[lane + j * w.nb] = -tauj * acc;
             if (lane == j) Tp[j + j * w.nb] = tauj;
             if (lane > j && lane < w.nb) Tp[lane + j * w.nb] = 0.0;
+            __threadfence();
         }
-    }
-    __syncthreads();
-    // (1) load the column, apply the right-update of the previous reflectors: b -= Y(:, 0:nbv-1) * V(i-2, 0:nbv-1)'
-    for (int rr = tid; rr < m; rr += LG_PT) {
-        double v = w.A[(size_t)(r0 + rr) + (size_t)c * n];
-        for (int q = 0; q < nbv; ++q) v -= Yp[rr + (size_t)q * n] * Vp[(nbv - 1) + (size_t)q * n];
-        b[rr] = v;
     }
     __syncthreads();
     // (2) left-apply (I - V T' V') to b
     if (nbv >= 1) {
-        // wv = V' b   (nbv reductions over m rows)
         double part[LG_NB];
 #pragma unroll
         for (int q = 0; q < LG_NB; ++q) part[q] = 0.0;
-        for (int rr = tid; rr < m; rr += LG_PT) {
-            const double bv = b[rr];
+        for (int rr = lo + tid; rr < hi; rr += LG_CT) {
+            const double bv = b[rr - lo];
 #pragma unroll
             for (int q = 0; q < LG_NB; ++q)
                 if (q < nbv) part[q] += Vp[rr + (size_t)q * n] * bv;
         }
-#pragma unroll
-        for (int q = 0; q < LG_NB; ++q) {
-            if (q < nbv) {
-                double s = warp_sum(part[q]);
-                if (lane == 0) red[warp * 32 + q] = s;
-            }
-        }
-        __syncthreads();
+        lg_block_sum32(part, nbv, red, xch, tid);
+        cluster.sync();                               // partial V'b of every rank (and rank 0's T column) visible
+        const double s = gather_vec();
         if (warp == 0) {
-            double s = 0.0;
-            if (lane < nbv)
-                for (int ww = 0; ww < LG_PT / 32; ++ww) s += red[ww * 32 + lane];
             // wv = T' * (V'b): T upper triangular -> (T' x)_q = sum_{r <= q} T[r][q] x_r
-            double x = s;
             double tq = 0.0;
             for (int r = 0; r < nbv; ++r) {
-                double xr = __shfl_sync(0xffffffffu, x, r);
-                if (lane < nbv && r <= lane) tq += Tp[r + lane * w.nb] * xr;
+                const double xr = __shfl_sync(0xffffffffu, s, r);
+                if (lane < nbv && r <= lane) tq += __ldcg(&Tp[r + lane * w.nb]) * xr;
             }
             if (lane < nbv) wv[lane] = tq;
         }
+        cluster.sync();                               // everybody has read xch: it may be overwritten
+        if (tid >= nbv && tid < LG_NB) wv[tid] = 0.0;
         __syncthreads();
-        for (int rr = tid; rr < m; rr += LG_PT) {
-            double v = b[rr];
-            for (int q = 0; q < nbv; ++q) v -= Vp[rr + (size_t)q * n] * wv[q];
-            b[rr] = v;
+        for (int rr = lo + tid; rr < hi; rr += LG_CT) {
+            double v = b[rr - lo];
+            double vrow[LG_NB];
+#pragma unroll
+            for (int q = 0; q < LG_NB; ++q) vrow[q] = (q < nbv) ? Vp[rr + (size_t)q * n] : 0.0;
+#pragma unroll
+            for (int q = 0; q < LG_NB; ++q) v -= vrow[q] * wv[q];
+            b[rr - lo] = v;
         }
         __syncthreads();
     }
     // (3) reflector on b[i-1 ..] (rows p+i ..): xLARFG as in src/householder.jl:12-54
     const int h = i - 1;                 // index of alpha within b
     const int tl = m - h - 1;            // tail length
-    double amax = 0.0;
-    for (int rr = h + 1 + tid; rr < m; rr += LG_PT) amax = fmax(amax, fabs(b[rr]));
-    amax = warp_max(amax);
-    if (lane == 0) red[warp] = amax;
-    __syncthreads();
-    amax = red[0];
-    for (int ww = 1; ww < LG_PT / 32; ++ww) amax = fmax(amax, red[ww]);
-    __syncthreads();
+    {
+        double amax = 0.0;
+        for (int rr = max(lo, h + 1) + tid; rr < hi; rr += LG_CT) amax = fmax(amax, fabs(b[rr - lo]));
+        amax = warp_max(amax);
+        if (lane == 0) red[warp] = amax;
+        __syncthreads();
+        if (tid == 0) {
+            double a = red[0];
+            for (int ww = 1; ww < LG_CT / 32; ++ww) a = fmax(a, red[ww]);
+            xch[32] = a;
+            xch[33] = (h >= lo && h < hi) ? b[h - lo] : 0.0;      // alpha lives in exactly one CTA
+        }
+    }
+    cluster.sync();
+    gather_scalars(true);
+    const double amax = bc[0], alpha = bc[1];
+    cluster.sync();
     double xnorm = 0.0;
-    if (amax > 0.0 && tl > 0) {
+    if (amax > 0.0 && tl > 0) {          // uniform over the cluster
         const double rs = 1.0 / amax;
         double ssq = 0.0;
-        for (int rr = h + 1 + tid; rr < m; rr += LG_PT) {
-            const double t = b[rr] * rs;
+        for (int rr = max(lo, h + 1) + tid; rr < hi; rr += LG_CT) {
+            const double t = b[rr - lo] * rs;
             ssq += t * t;
         }
         ssq = warp_sum(ssq);
         if (lane == 0) red[warp] = ssq;
         __syncthreads();
-        ssq = 0.0;
-        for (int ww = 0; ww < LG_PT / 32; ++ww) ssq += red[ww];
-        __syncthreads();
-        xnorm = amax * sqrt(ssq);
+        if (tid == 0) {
+            double q = 0.0;
+            for (int ww = 0; ww < LG_CT / 32; ++ww) q += red[ww];
+            xch[32] = q;
+        }
+        if (tid == 0) xch[33] = 0.0;
+        cluster.sync();
+        gather_scalars(false);
+        xnorm = amax * sqrt(bc[0]);
+        cluster.sync();
     }
-    const double alpha = b[h];
     double tau = 0.0, beta = alpha, scal = 0.0;
     if (xnorm != 0.0) {
         beta = -copysign(hypot(alpha, xnorm), alpha);
@@ -166,17 +256,18 @@ __global__ void __launch_bounds__(LG_PT) lg_panel_col_kernel(LargeWork w, int p,
         scal = 1.0 / (alpha - beta);
     }
     // write back: H entries of column c (rows r0 .. p+i), reflector tail into A and into the dense V block
-    for (int rr = tid; rr < m; rr += LG_PT) {
+    for (int rr = lo + tid; rr < hi; rr += LG_CT) {
         double a_out, v_out;
-        if (rr < h) { a_out = b[rr]; v_out = 0.0; }
+        const double bv = b[rr - lo];
+        if (rr < h) { a_out = bv; v_out = 0.0; }
         else if (rr == h) { a_out = beta; v_out = 1.0; }
-        else { v_out = b[rr] * scal; a_out = v_out; }
+        else { v_out = bv * scal; a_out = v_out; }
         w.A[(size_t)(r0 + rr) + (size_t)c * n] = a_out;
         Vp[rr + (size_t)h * n] = v_out;
         w.vcur[r0 + rr] = v_out;
-        b[rr] = v_out;
+        b[rr - lo] = v_out;
     }
-    if (tid == 0) {
+    if (rank == 0 && tid == 0) {
         w.tau[c] = tau;
         w.tsave[w.nb] = tau;
     }
@@ -186,25 +277,17 @@ __global__ void __launch_bounds__(LG_PT) lg_panel_col_kernel(LargeWork w, int p,
         double part[LG_NB];
 #pragma unroll
         for (int q = 0; q < LG_NB; ++q) part[q] = 0.0;
-        for (int rr = h + tid; rr < m; rr += LG_PT) {
-            const double bv = b[rr];
+        for (int rr = max(lo, h) + tid; rr < hi; rr += LG_CT) {
+            const double bv = b[rr - lo];
 #pragma unroll
             for (int q = 0; q < LG_NB; ++q)
                 if (q < h) part[q] += Vp[rr + (size_t)q * n] * bv;
         }
-#pragma unroll
-        for (int q = 0; q < LG_NB; ++q) {
-            if (q < h) {
-                double s = warp_sum(part[q]);
-                if (lane == 0) red[warp * 32 + q] = s;
-            }
-        }
-        __syncthreads();
-        if (warp == 0 && lane < h) {
-            double s = 0.0;
-            for (int ww = 0; ww < LG_PT / 32; ++ww) s += red[ww * 32 + lane];
-            w.tsave[lane] = s;
-        }
+        lg_block_sum32(part, h, red, xch, tid);
+        cluster.sync();
+        const double tsum = gather_vec();
+        if (rank == 0 && warp == 0 && lane < h) w.tsave[lane] = tsum;
+        cluster.sync();                               // remote shared memory stays valid until every read is done
     }
 }
 
@@ -319,8 +402,21 @@ inline int lg_gehrd(LargeWork& w, double* Q, cudaStream_t s, std::string* err) {
     const size_t nn = (size_t)n * n;
     lg_zero_kernel<<<(unsigned)((nn + 255) / 256), 256, 0, s>>>(w.V, nn);
     note_launch();
-    const size_t smem_panel = ((size_t)((n + 31) & ~31) + 32 * 32 + nb + 8) * sizeof(double);
+    const size_t smem_panel = ((size_t)((((n + LG_NC - 1) / LG_NC) + 31) & ~31) + (LG_CT / 32) * 32 + 40 + 3 * LG_NB + 8) * sizeof(double);   // b | red | xch | wv, ts, vr | bc
     LG_TRY(cudaFuncSetAttribute(lg_panel_col_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_panel));
+    LG_TRY(cudaFuncSetAttribute(lg_panel_col_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    cudaLaunchConfig_t pcfg = {};
+    cudaLaunchAttribute pattr[1];
+    pattr[0].id = cudaLaunchAttributeClusterDimension;
+    pattr[0].val.clusterDim.x = LG_NC;
+    pattr[0].val.clusterDim.y = 1;
+    pattr[0].val.clusterDim.z = 1;
+    pcfg.gridDim = dim3(LG_NC, 1, 1);
+    pcfg.blockDim = dim3(LG_CT, 1, 1);
+    pcfg.dynamicSmemBytes = smem_panel;
+    pcfg.stream = s;
+    pcfg.attrs = pattr;
+    pcfg.numAttrs = 1;
     int npanels = 0;
     for (int p = 0; p < n - 1; p += nb, ++npanels) {
         const int ib = (n - 1 - p < nb) ? n - 1 - p : nb;
@@ -328,7 +424,7 @@ inline int lg_gehrd(LargeWork& w, double* Q, cudaStream_t s, std::string* err) {
         lg_zero_kernel<<<(nb * nb + 255) / 256, 256, 0, s>>>(w.T + (size_t)npanels * nb * nb, (size_t)nb * nb);
         note_launch();
         for (int i = 1; i <= ib; ++i) {
-            lg_panel_col_kernel<<<1, LG_PT, smem_panel, s>>>(w, p, i);
+            LG_TRY(cudaLaunchKernelEx(&pcfg, lg_panel_col_kernel, w, p, i));
             note_launch();
             // y = A(r0.., p+i ..) * v    (v has its leading 1 at row p+i)
             const int rowblocks = (m + 1 + LG_GEMV_ROWS - 1) / LG_GEMV_ROWS;

@@ -472,6 +472,7 @@ struct StageBKernel {
     size_t smem;
     int per_cta;
     const char* name;
+    int threads = 32;
 };
 template <class T, int CPL> StageBKernel stage_b_select(int n) {
     StageBKernel k;
@@ -567,7 +568,7 @@ template <class T, int CPL> int launch_fast3(const BatchedParams& p_in, int dev_
         int perB = 0, perR = 0;
         F3_TRY(cudaFuncSetAttribute(kB, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB), "qrlog kernel setup");
         F3_TRY(cudaFuncSetAttribute(kB, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "qrlog kernel setup");
-        F3_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perB, kB, 32, smemB), "qrlog kernel occupancy");
+        F3_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perB, kB, sb.threads, smemB), "qrlog kernel occupancy");
         F3_TRY(cudaFuncSetAttribute(kC, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemC), "zreplay kernel setup");
         F3_TRY(cudaFuncSetAttribute(kC, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "zreplay kernel setup");
         F3_TRY(cudaFuncSetAttribute(kR, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemR), "qr kernel setup");
@@ -613,7 +614,7 @@ template <class T, int CPL> int launch_fast3(const BatchedParams& p_in, int dev_
             p.counter = ctr;
             long long grid = (long long)perB * dev_sms;
             if (grid > (cn + sb.per_cta - 1) / sb.per_cta) grid = (cn + sb.per_cta - 1) / sb.per_cta;
-            kB<<<(unsigned)grid, 32, smemB, stream>>>(p);
+            kB<<<(unsigned)grid, sb.threads, smemB, stream>>>(p);
             note_launch();
             stage_timing_mark(2, stream);
             if (wantZ) {

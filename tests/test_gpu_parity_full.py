@@ -344,7 +344,7 @@ def test_pipeline_budget_and_release(gs, O, monkeypatch):
     monkeypatch.delenv("GSCHUR_PIPE_BUDGET_MB")
     assert np.array_equal(S0.T, S1.T) and np.array_equal(S0.Z, S1.Z) and np.array_equal(S0.values, S1.values)
     assert gs.release_workspace() == 0
-    monkeypatch.setenv("GSCHUR_HOST_REGISTER", "0")
+    monkeypatch.setenv("GSCHUR_HOST_REGISTER", "1")
     S2 = gs.gschur(A)
     assert np.array_equal(S0.T, S2.T) and np.array_equal(S0.Z, S2.Z)
     for b in (0, batch - 1):
