@@ -31,7 +31,7 @@ from ._lib import C64, CDD, DD, F64
 __all__ = [
     "gschur", "gschur_", "gschur_batched_", "schur", "schur_", "eigvals", "eigvals_", "hessenberg", "hessenberg_",
     "gschur_hess_", "gschur_device_", "Schur", "Hessenberg", "UnconvergedException", "DimensionMismatch",
-    "ArgumentError", "DDArray", "CDDArray", "F64", "C64", "DD", "CDD", "device_count", "launch_count", "release_workspace",
+    "ArgumentError", "DDArray", "CDDArray", "F64", "C64", "DD", "CDD", "device_count", "launch_count", "release_workspace", "geigvecs", "eigen",
 ]
 
 
@@ -119,6 +119,17 @@ def measure_fp64_peak():
     rc = _lib.lib().gschur_cuda_measure_fp64_peak(ctypes.byref(t), ctypes.byref(ms))
     if rc != 0:
         raise RuntimeError(f"gschur_cuda_measure_fp64_peak failed: {rc}")
+    return t.value, ms.value
+
+
+def measure_dmma_peak():
+    """(TFLOP/s, ms) of a DMMA-only (mma.sync.m8n8k4.f64) micro-kernel: the FP64 tensor roofline denominator of the
+    large-matrix path's GEMM updates."""
+    t = ctypes.c_double(0.0)
+    ms = ctypes.c_double(0.0)
+    rc = _lib.lib().gschur_cuda_measure_dmma_peak(ctypes.byref(t), ctypes.byref(ms))
+    if rc != 0:
+        raise RuntimeError(f"gschur_cuda_measure_dmma_peak failed: {rc}")
     return t.value, ms.value
 
 
@@ -351,6 +362,30 @@ def gschur_hess_(H, Z=None, maxiter=None, checksd=True):
             raise DimensionMismatch("second dimension of Z must match H")
     flags = _lib.FLAG_HESS_INPUT | (_lib.FLAG_CHECK_SUBDIAG if checksd else 0)
     return gschur_(H, wantZ=Z is not None, scale=False, maxiter=maxiter, flags=flags, Z=Z)
+
+
+def geigvecs(S, left=False, normalize=True):
+    """geigvecs(S; left) (src/vectors.jl:12-20): eigenvectors from a Schur decomposition `S` — _geigvecs! /
+    _gleigvecs! on (S.T, S.Z) followed by _enormalize!.  ComplexF64, one matrix or a batch (trailing axis)."""
+    T, Z = S.T, S.Z
+    kind, lead, n, batch = _kind_and_shape(T)
+    if kind != C64:
+        raise ArgumentError("eigenvectors from the Schur form are implemented for ComplexF64 only")
+    nb = 1 if batch is None else batch
+    haveZ = Z is not None and Z.size > 0
+    V = np.zeros_like(T, order="F")
+    rc = _lib.lib().gschur_cuda_eigvecs_batched(kind, n, nb, _ptr(T), n, n * n, _ptr(Z) if haveZ else None, n, n * n,
+                                               _ptr(V), n, n * n, int(bool(left)), 0 if normalize else 0x10)
+    if rc != 0:
+        raise RuntimeError(f"libgschur_cuda error {rc}: {_lib.lib().gschur_cuda_eigvecs_last_error().decode()}")
+    return V
+
+
+def eigen(A, **kw):
+    """eigen(A) without balancing (src/pirates.jl:63-90 with permute = scale = false): (values, vectors) of a ComplexF64
+    matrix or batch: gschur! followed by the eigenvectors of the Schur form, both on the GPU."""
+    S = gschur(A, **kw)
+    return S.values, geigvecs(S)
 
 
 def release_workspace():

@@ -27,10 +27,13 @@ EXPORTS = [
     "gschur_cuda_batched_async",
     "gschur_cuda_hessenberg_batched",
     "gschur_cuda_measure_fp64_peak",
+    "gschur_cuda_measure_dmma_peak",
     "gschur_cuda_measure_l2_bandwidth",
     "gschur_cuda_stage_timing",
     "gschur_cuda_stage_timing3",
     "gschur_cuda_release_workspace",
+    "gschur_cuda_eigvecs_batched",
+    "gschur_cuda_eigvecs_last_error",
     "gschur_cuda_hessenberg_large",
     "gschur_cuda_large",
     "gschur_cuda_dgemm",
@@ -73,6 +76,9 @@ def lib():
         L.gschur_cuda_measure_l2_bandwidth.argtypes = [vp, vp]
         L.gschur_cuda_measure_l2_bandwidth.restype = ci
         cd = ctypes.c_double
+        L.gschur_cuda_eigvecs_batched.argtypes = [ci, ci, i64, vp, ci, i64, vp, ci, i64, vp, ci, i64, ci, u32]
+        L.gschur_cuda_eigvecs_batched.restype = ci
+        L.gschur_cuda_eigvecs_last_error.restype = ctypes.c_char_p
         L.gschur_cuda_hessenberg_large.argtypes = [ci, vp, ci, vp, vp, ci, u32]
         L.gschur_cuda_hessenberg_large.restype = ci
         L.gschur_cuda_stage_timing.argtypes = [ci, vp, vp]

@@ -46,7 +46,66 @@ __global__ void __launch_bounds__(256) l2_stream_kernel(uint4* buf, size_t n4, i
         }
     }
 }
+// FP64 tensor (DMMA) probe: independent mma.sync.m8n8k4.f64 chains, operands in registers — the BLAS3 denominator of
+// the large-matrix path (dgemm.cuh).  8 accumulator pairs per warp, 512 flop per instruction.
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a, double b) {
+    double c[8][2];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+        c[u][0] = threadIdx.x * 1e-3 + u;
+        c[u][1] = c[u][0] + 0.5;
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                             : "+d"(c[u][0]), "+d"(c[u][1])
+                             : "d"(a), "d"(b));
+        }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += c[u][0] + c[u][1];
+    if (s == 123.456) out[0] = s;
+}
 }  // namespace
+
+extern "C" int gschur_cuda_measure_dmma_peak(double* tflops, double* ms_out) {
+    int dev = 0;
+    if (!tflops) return GSCHUR_ERR_ARG;
+    if (cudaGetDevice(&dev) != cudaSuccess) return GSCHUR_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return GSCHUR_ERR_CUDA;
+    double* d = nullptr;
+    if (cudaMalloc(&d, 8) != cudaSuccess) return GSCHUR_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 2048;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        dmma_peak_kernel<<<blocks, threads>>>(d, iters, 1e-9, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) {
+            cudaFree(d);
+            return GSCHUR_ERR_CUDA;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    // per warp and instruction: m8n8k4 = 256 FMA = 512 flop; 32 instructions per iteration
+    const double flops = 512.0 * 32.0 * (double)iters * (double)(threads / 32) * (double)blocks;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return 0;
+}
 
 extern "C" int gschur_cuda_measure_fp64_peak(double* tflops, double* ms_out) {
     int dev = 0;

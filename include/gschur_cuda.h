@@ -101,6 +101,12 @@ int gschur_cuda_batched_async(int kind, int n, int64_t batch,
 int gschur_cuda_measure_fp64_peak(double* tflops, double* ms);
 
 /*
+ * Measures the FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) peak of the current device with register-resident
+ * operands: the BLAS3 denominator of the large-matrix path's GEMM updates.  *tflops, *ms (NULL ok) as above.
+ */
+int gschur_cuda_measure_dmma_peak(double* tflops, double* ms);
+
+/*
  * Measures the L2 streaming bandwidth of the current device: a 38.8 MB buffer (resident in the 126 MB L2) is read
  * and written back 64 times with L1-bypassing 16-byte accesses, the access pattern of stage B's Z stream (DESIGN.md
  * section 6: the L2 ceiling behind the FP64 one).  *gbs receives (bytes read + bytes written) / s / 1e9, *ms (NULL
@@ -142,6 +148,20 @@ int gschur_cuda_hessenberg_batched(int kind, int n, int64_t batch,
                                    void* tau,
                                    void* Q, int ldq, int64_t strideQ,
                                    const int* devices, int ndev, uint32_t flags);
+
+/*
+ * Eigenvectors from the Schur form, batched, ComplexF64 (kind 1) only.
+ * Replaces geigvecs(S; left) = _geigvecs!(S.T, S.Z) / _gleigvecs!(S.T, S.Z) + _enormalize!
+ * (src/vectors.jl:12-20, 45-131, 372-460; src/util.jl:128-461, 572-592) — the vectors eigen! returns
+ * (src/pirates.jl:63-90) — for the T, Z that gschur_cuda_batched left on the device or the host.
+ *   T    in: upper triangular Schur forms (not modified)      Z  in: Schur vectors (NULL: eigenvectors of T itself)
+ *   V    out: n x n per matrix, column k = eigenvector of T[k,k]; unit 2-norm with the largest component real
+ *        (flag 0x10: skip _enormalize!, i.e. the raw _geigvecs! scaling with max abs1 component 1)
+ *   left != 0: left eigenvectors.   flags: GSCHUR_FLAG_DEVICE_PTRS.
+ */
+int gschur_cuda_eigvecs_batched(int kind, int n, int64_t batch, const void* T, int ldt, int64_t strideT, const void* Z,
+                                int ldz, int64_t strideZ, void* V, int ldv, int64_t strideV, int left, uint32_t flags);
+const char* gschur_cuda_eigvecs_last_error(void);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Regime (2): ONE large Float64 matrix on one GPU (BASELINE config 4).  Host or device pointers

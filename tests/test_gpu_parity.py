@@ -383,6 +383,8 @@ def test_roofline_probes(gs):
     assert 5.0 < t < 80.0 and ms > 0
     g, ms = gs.measure_l2_bandwidth()
     assert 2000.0 < g < 40000.0 and ms > 0
+    d, ms = gs.measure_dmma_peak()         # FP64 tensor peak (nominal 37-40 TFLOP/s on a B200)
+    assert 5.0 < d < 90.0 and ms > 0
 
 
 def test_dmma_gemm(gs):
