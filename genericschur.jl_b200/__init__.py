@@ -31,7 +31,7 @@ from ._lib import C64, CDD, DD, F64
 __all__ = [
     "gschur", "gschur_", "gschur_batched_", "schur", "schur_", "eigvals", "eigvals_", "hessenberg", "hessenberg_",
     "gschur_hess_", "gschur_device_", "Schur", "Hessenberg", "UnconvergedException", "DimensionMismatch",
-    "ArgumentError", "DDArray", "CDDArray", "F64", "C64", "DD", "CDD", "device_count", "launch_count", "release_workspace", "geigvecs", "eigen",
+    "ArgumentError", "DDArray", "CDDArray", "F64", "C64", "DD", "CDD", "device_count", "launch_count", "release_workspace", "geigvecs", "eigen", "eigen_", "balance", "balance_", "balancer_lmul_", "triangularize", "Balancer",
 ]
 
 
@@ -386,6 +386,119 @@ def eigen(A, **kw):
     matrix or batch: gschur! followed by the eigenvectors of the Schur form, both on the GPU."""
     S = gschur(A, **kw)
     return S.values, geigvecs(S)
+
+
+class Balancer:
+    """Mirror of GenericSchur.Balancer (src/balance.jl:3-10): ilo, ihi, prow, pcol, D, trivial (batched: trailing axis)."""
+
+    def __init__(self, ilo, ihi, D, perm, trivial):
+        self.ilo, self.ihi, self.D, self.perm, self.trivial = ilo, ihi, D, perm, trivial
+
+    @property
+    def prow(self):
+        return self.perm[: self.ilo - 1] if np.ndim(self.ilo) == 0 else None
+
+    @property
+    def pcol(self):
+        return self.perm[self.ihi:] if np.ndim(self.ihi) == 0 else None
+
+    def _raw(self):
+        ii = np.stack([np.atleast_1d(self.ilo), np.atleast_1d(self.ihi), np.atleast_1d(self.trivial).astype(np.int32)],
+                      axis=1).astype(np.int32)
+        return np.ascontiguousarray(ii), np.asfortranarray(self.D, dtype=np.float64), np.asfortranarray(self.perm, dtype=np.int32)
+
+
+def balance_(A, scale=True, permute=True):
+    """balance!(A; scale, permute) => (Abal, B::Balancer)   (src/balance.jl:33-199).  Float64 / ComplexF64, one matrix or
+    a batch (trailing axis); A is overwritten."""
+    kind, lead, n, batch = _kind_and_shape(A)
+    if kind not in (F64, C64):
+        raise ArgumentError("balance! is implemented for Float64 and ComplexF64")
+    if not (A.flags.f_contiguous and A.flags.writeable):
+        raise ArgumentError("A must be a writeable Fortran-ordered (column-major) array")
+    nb = 1 if batch is None else batch
+    D = np.zeros((n, nb), order="F")
+    perm = np.zeros((n, nb), dtype=np.int32, order="F")
+    ii = np.zeros((nb, 3), dtype=np.int32)
+    info = np.zeros(nb, dtype=np.int32)
+    rc = _lib.lib().gschur_cuda_balance_batched(kind, n, nb, _ptr(A), n, n * n, _ptr(D), _ptr(ii), _ptr(perm), _ptr(info),
+                                               int(bool(scale)), int(bool(permute)), 0)
+    if rc != 0:
+        raise RuntimeError(f"libgschur_cuda error {rc}: {_lib.lib().gschur_cuda_balance_last_error().decode()}")
+    if (info != 0).any():
+        raise RuntimeError("NaN encountered while balancing")
+    if batch is None:
+        return A, Balancer(int(ii[0, 0]), int(ii[0, 1]), D[:, 0], perm[:, 0], bool(ii[0, 2]))
+    return A, Balancer(ii[:, 0].copy(), ii[:, 1].copy(), D, perm, ii[:, 2].astype(bool))
+
+
+def balance(A, **kw):
+    return balance_(_copy_f(np.asarray(A)), **kw)
+
+
+def balancer_lmul_(B, V, inverse=False):
+    """lmul!(B::Balancer, V) (right eigenvectors) / ldiv!(B, V) (inverse=True, left eigenvectors), src/balance.jl:203-260"""
+    kind, lead, n, batch = _kind_and_shape(V)
+    nb = 1 if batch is None else batch
+    ii, D, perm = B._raw()
+    rc = _lib.lib().gschur_cuda_balance_apply_batched(kind, n, nb, _ptr(V), n, n * n, _ptr(D), _ptr(ii), _ptr(perm),
+                                                     int(bool(inverse)), 0)
+    if rc != 0:
+        raise RuntimeError(f"libgschur_cuda error {rc}: {_lib.lib().gschur_cuda_balance_last_error().decode()}")
+    return V
+
+
+def triangularize(S):
+    """triangularize(S::Schur{<:Real}) => Schur{Complex} (src/triang.jl:9-43), one matrix or a batch."""
+    T, Z = S.T, S.Z
+    kind, lead, n, batch = _kind_and_shape(T)
+    if kind != F64:
+        raise ArgumentError("triangularize takes a real (Float64) Schur decomposition")
+    nb = 1 if batch is None else batch
+    haveZ = Z is not None and Z.size > 0
+    shape = T.shape
+    Tc = np.zeros(shape, dtype=np.complex128, order="F")
+    Zc = np.zeros(shape, dtype=np.complex128, order="F") if haveZ else None
+    w = np.zeros((n,) if batch is None else (n, batch), dtype=np.complex128, order="F")
+    rc = _lib.lib().gschur_cuda_triangularize_batched(n, nb, _ptr(T), n, n * n, _ptr(Z) if haveZ else None, n, n * n,
+                                                     _ptr(Tc), _ptr(Zc), _ptr(w), 0)
+    if rc != 0:
+        raise RuntimeError(f"libgschur_cuda error {rc}: {_lib.lib().gschur_cuda_balance_last_error().decode()}")
+    return Schur(Tc, Zc if haveZ else np.zeros((0, 0), dtype=np.complex128), w)
+
+
+def eigen_(A, permute=True, scale=True):
+    """eigen!(A; permute, scale) (src/pirates.jl:63-90, the path without condition numbers): balance!, gschur!
+    (+ triangularize for Float64), eigenvectors of the Schur form, lmul!(B, v), _enormalize! — every step on the GPU.
+    Returns (values, vectors), unsorted (sortby = nothing)."""
+    kind, lead, n, batch = _kind_and_shape(A)
+    if kind not in (F64, C64):
+        raise ArgumentError("eigen! is implemented for Float64 and ComplexF64")
+    B = None
+    if permute or scale:
+        A, B = balance_(A, scale=scale, permute=permute)
+    S = gschur_(A)
+    if kind == F64:
+        S = triangularize(S)
+    v = geigvecs(S, normalize=False)
+    if B is not None:
+        balancer_lmul_(B, v)
+    v = _enormalize_(v)
+    return S.values, v
+
+
+def _enormalize_(v):
+    """_enormalize! (src/util.jl:572-592) through the eigenvector kernel's normalisation pass (identity T, Z = v)"""
+    kind, lead, n, batch = _kind_and_shape(v)
+    nb = 1 if batch is None else batch
+    eye = np.zeros_like(v, order="F")
+    idx = np.arange(n)
+    eye[idx, idx, ...] = 1.0
+    out = np.zeros_like(v, order="F")
+    rc = _lib.lib().gschur_cuda_eigvecs_batched(C64, n, nb, _ptr(eye), n, n * n, _ptr(v), n, n * n, _ptr(out), n, n * n, 0, 0)
+    if rc != 0:
+        raise RuntimeError(f"libgschur_cuda error {rc}: {_lib.lib().gschur_cuda_eigvecs_last_error().decode()}")
+    return out
 
 
 def release_workspace():

@@ -34,6 +34,10 @@ EXPORTS = [
     "gschur_cuda_release_workspace",
     "gschur_cuda_eigvecs_batched",
     "gschur_cuda_eigvecs_last_error",
+    "gschur_cuda_balance_batched",
+    "gschur_cuda_balance_apply_batched",
+    "gschur_cuda_triangularize_batched",
+    "gschur_cuda_balance_last_error",
     "gschur_cuda_hessenberg_large",
     "gschur_cuda_large",
     "gschur_cuda_dgemm",
@@ -79,6 +83,13 @@ def lib():
         L.gschur_cuda_eigvecs_batched.argtypes = [ci, ci, i64, vp, ci, i64, vp, ci, i64, vp, ci, i64, ci, u32]
         L.gschur_cuda_eigvecs_batched.restype = ci
         L.gschur_cuda_eigvecs_last_error.restype = ctypes.c_char_p
+        L.gschur_cuda_balance_batched.argtypes = [ci, ci, i64, vp, ci, i64, vp, vp, vp, vp, ci, ci, u32]
+        L.gschur_cuda_balance_batched.restype = ci
+        L.gschur_cuda_balance_apply_batched.argtypes = [ci, ci, i64, vp, ci, i64, vp, vp, vp, ci, u32]
+        L.gschur_cuda_balance_apply_batched.restype = ci
+        L.gschur_cuda_triangularize_batched.argtypes = [ci, i64, vp, ci, i64, vp, ci, i64, vp, vp, vp, u32]
+        L.gschur_cuda_triangularize_batched.restype = ci
+        L.gschur_cuda_balance_last_error.restype = ctypes.c_char_p
         L.gschur_cuda_hessenberg_large.argtypes = [ci, vp, ci, vp, vp, ci, u32]
         L.gschur_cuda_hessenberg_large.restype = ci
         L.gschur_cuda_stage_timing.argtypes = [ci, vp, vp]

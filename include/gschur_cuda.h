@@ -163,6 +163,27 @@ int gschur_cuda_eigvecs_batched(int kind, int n, int64_t batch, const void* T, i
                                 int ldz, int64_t strideZ, void* V, int ldv, int64_t strideV, int left, uint32_t flags);
 const char* gschur_cuda_eigvecs_last_error(void);
 
+/*
+ * Balancing pre-step and its back-transformation, triangularize post-step, batched,
+ * Float64 / ComplexF64 (kinds 0, 1).  flags: GSCHUR_FLAG_DEVICE_PTRS.  Errors: gschur_cuda_balance_last_error().
+ *
+ * gschur_cuda_balance_batched       balance!(A; scale, permute) src/balance.jl:33-199: A is overwritten by the balanced
+ *     matrix; per matrix D (n doubles, the diagonal similarity), ilo_ihi_trivial (3 ints: ilo, ihi, trivial flag of the
+ *     Balancer) and perm (n ints: the exchange targets `sp`, 1-based, 0 where unused; prow = perm[0:ilo-1],
+ *     pcol = perm[ihi:n]).  info (NULL ok): 0, or -5 for the reference's error("NaN encountered while balancing").
+ * gschur_cuda_balance_apply_batched lmul!(B, V) (inverse = 0: right eigenvectors of the balanced matrix -> those of
+ *     A) / ldiv!(B, V) (inverse = 1: left eigenvectors) src/balance.jl:203-260, V n x n per matrix, in place.
+ * gschur_cuda_triangularize_batched triangularize(S::Schur{<:Real}) src/triang.jl:9-43: the complex upper triangular
+ *     Schur form (Tc, Zc: n x n ComplexF64 each, leading dimension n; w: n eigenvalues) of a standardised real one.
+ */
+int gschur_cuda_balance_batched(int kind, int n, int64_t batch, void* A, int lda, int64_t strideA, double* D,
+                                int32_t* ilo_ihi_trivial, int32_t* perm, int32_t* info, int scale, int permute, uint32_t flags);
+int gschur_cuda_balance_apply_batched(int kind, int n, int64_t batch, void* V, int ldv, int64_t strideV, const double* D,
+                                      const int32_t* ilo_ihi_trivial, const int32_t* perm, int inverse, uint32_t flags);
+int gschur_cuda_triangularize_batched(int n, int64_t batch, const double* T, int ldt, int64_t strideT, const double* Z, int ldz,
+                                      int64_t strideZ, void* Tc, void* Zc, void* w, uint32_t flags);
+const char* gschur_cuda_balance_last_error(void);
+
 /* ------------------------------------------------------------------------------------------------------------
  * Regime (2): ONE large Float64 matrix on one GPU (BASELINE config 4).  Host or device pointers
  * (GSCHUR_FLAG_DEVICE_PTRS), blocking.

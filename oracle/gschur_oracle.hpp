@@ -915,4 +915,166 @@ template <class R> void eigvalscond_triu(Mat<Cx<R>> T, R* s) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// balance!(A; scale, permute) — src/balance.jl:33-199 (algo = :pr, p = 1) — and lmul!(B, V) / ldiv!(B, V) :203-260.
+// Float64 / ComplexF64 only.  The two-norms are formed the way the CUDA kernel documents (per-"lane" partial sums
+// over indices of stride 32, xor butterfly, unfused operations; amax = sqrt(max |x|^2) as _findamax for complex,
+// src/norm1est.jl:76-100): norm(view, 2) of the reference differs from this by rounding only, and with the
+// operation order fixed the power-of-two decisions of the two implementations can be compared exactly.
+// ---------------------------------------------------------------------------------------------
+inline double bal_abs2(double x) { return x * x; }
+inline double bal_abs2(const Cx<double>& x) { return x.re * x.re + x.im * x.im; }
+inline double bal_sabs2(double x, double s) { double t = x * s; return t * t; }
+inline double bal_sabs2(const Cx<double>& x, double s) { double a = x.re * s, b = x.im * s; return a * a + b * b; }
+inline double bal_mod(double x) { return std::fabs(x); }
+inline double bal_mod(const Cx<double>& x) { return std::hypot(x.re, x.im); }
+inline bool bal_nz(double x) { return x != 0.0; }
+inline bool bal_nz(const Cx<double>& x) { return x.re != 0.0 || x.im != 0.0; }
+inline double bal_times(double x, double f) { return x * f; }
+inline Cx<double> bal_times(const Cx<double>& x, double f) { return Cx<double>(x.re * f, x.im * f); }
+
+template <class E> void bal_norms(const E* x, long st, int len, double& amax, double& nrm) {
+    double part[32];
+    auto butterfly_sum = [&]() {
+        for (int m = 16; m >= 1; m >>= 1) {
+            double nw[32];
+            for (int l = 0; l < 32; ++l) nw[l] = part[l] + part[l ^ m];
+            for (int l = 0; l < 32; ++l) part[l] = nw[l];
+        }
+        return part[0];
+    };
+    double m2 = 0.0;
+    for (int t = 0; t < len; ++t) m2 = std::fmax(m2, bal_abs2(x[(long)t * st]));
+    amax = std::sqrt(m2);
+    if (!(amax > 0.0) || !(amax < 1.7976931348623157e308)) {
+        double mx = 0.0;
+        bool nan = false;
+        for (int t = 0; t < len; ++t) {
+            double a = bal_mod(x[(long)t * st]);
+            if (a != a) nan = true;
+            mx = std::fmax(mx, a);
+        }
+        amax = nan ? std::nan("") : mx;
+    }
+    if (!(amax > 0.0)) {
+        nrm = amax;
+        return;
+    }
+    const double s = 1.0 / amax;
+    for (int l = 0; l < 32; ++l) part[l] = 0.0;
+    for (int t = 0; t < len; ++t) part[t & 31] = part[t & 31] + bal_sabs2(x[(long)t * st], s);
+    nrm = amax * std::sqrt(butterfly_sum());
+}
+
+// returns 0, or -5 for the reference's error("NaN encountered while balancing")
+template <class E> int balance(Mat<E> A, bool scale, bool permute, double* D, int* sp, int& ilo, int& ihi, bool& trivial) {
+    const int n = A.n;
+    for (int i = 0; i < n; ++i) { D[i] = 1.0; sp[i] = 0; }
+    ilo = 1; ihi = n; trivial = true;
+    auto swap_rc = [&](int js, int ms) {
+        for (int i = 1; i <= ihi; ++i) std::swap(A(i, js), A(i, ms));
+        for (int i = ilo; i <= n; ++i) std::swap(A(js, i), A(ms, i));
+    };
+    if (permute) {
+        ihi = n + 1;
+        while (ihi > 1) {
+            ihi -= 1;
+            bool exch = false;
+            int js = 0, ms = 0;
+            for (int j = ihi; j >= 1; --j) {
+                exch = true;
+                js = j;
+                for (int i = 1; i <= ihi; ++i) {
+                    if (i == j) continue;
+                    if (bal_nz(A(j, i))) exch = false;
+                }
+                if (exch) { ms = ihi; break; }
+            }
+            if (exch) {
+                sp[ms - 1] = js;
+                if (js != ms) { trivial = false; swap_rc(js, ms); }
+            } else break;
+        }
+        if (ihi > 1) {
+            ilo = 0;
+            while (ilo < n) {
+                ilo += 1;
+                bool exch = false;
+                int js = 0, ms = 0;
+                for (int j = ilo; j <= ihi; ++j) {
+                    js = j;
+                    exch = true;
+                    for (int i = ilo; i <= ihi; ++i) {
+                        if (i == j) continue;
+                        if (bal_nz(A(i, j))) exch = false;
+                    }
+                    if (exch) { ms = ilo; break; }
+                }
+                if (exch) {
+                    sp[ms - 1] = js;
+                    if (ms != js) { trivial = false; swap_rc(js, ms); }
+                } else break;
+            }
+        }
+    }
+    if (scale) {
+        const double beta = 2.0, factor = 0.95;
+        const double sfmin1 = 2.2250738585072014e-308 / 2.220446049250313e-16;
+        const double sfmin2 = sfmin1 * beta, sfmax2 = 1.0 / sfmin2;
+        bool converged = false;
+        int guard = 0;
+        while (!converged && guard++ < 10000) {
+            converged = true;
+            for (int i = ilo; i <= ihi; ++i) {
+                double c, r, ca, ra;
+                const int len = ihi - ilo + 1;
+                bal_norms<E>(&A(ilo, i), 1, len, ca, c);
+                bal_norms<E>(&A(i, ilo), A.ld, len, ra, r);
+                if (c == 0.0 || r == 0.0) continue;
+                double g = r / beta;
+                const double s = c + r;
+                double f = 1.0;
+                while (c < r / beta) {
+                    if (c >= g || (std::fmax(f, std::fmax(c, ca)) >= sfmax2) || (std::fmin(r, std::fmin(g, ra)) <= sfmin2)) break;
+                    const double chk = c + f + ca + r + g + ra;
+                    if (chk != chk) return -5;
+                    f *= beta; c *= beta; ca *= beta; r /= beta; g /= beta; ra /= beta;
+                }
+                g = c / beta;
+                while (r <= c / beta) {
+                    if ((g < r) || (std::fmax(r, ra) >= sfmax2) || (std::fmin(std::fmin(f, c), std::fmin(g, ca)) <= sfmin2)) break;
+                    f /= beta; c /= beta; g /= beta; ca /= beta; r *= beta; ra *= beta;
+                }
+                if (f != 1.0) trivial = false;
+                if (c + r >= factor * s) continue;
+                converged = false;
+                D[i - 1] *= f;
+                const double rf = 1.0 / f;
+                for (int j = ilo; j <= n; ++j) A(i, j) = bal_times(A(i, j), rf);
+                for (int j = 1; j <= ihi; ++j) A(j, i) = bal_times(A(j, i), f);
+            }
+        }
+    }
+    return 0;
+}
+
+// lmul!(B, V) (inv = false) / ldiv!(B, V) (inv = true), src/balance.jl:203-260
+template <class E> void balance_apply(Mat<E> V, const double* D, const int* sp, int ilo, int ihi, bool trivial, bool inv) {
+    const int n = V.n;
+    if (trivial) return;
+    if (ilo != ihi)
+        for (int j = 1; j <= n; ++j)
+            for (int i = 1; i <= n; ++i) V(i, j) = bal_times(V(i, j), inv ? 1.0 / D[i - 1] : D[i - 1]);
+    for (int j = ilo - 1; j >= 1; --j) {
+        const int m = sp[j - 1];
+        if (m == j) continue;
+        for (int i = 1; i <= n; ++i) std::swap(V(j, i), V(m, i));
+    }
+    for (int j = ihi + 1; j <= n; ++j) {
+        const int m = sp[j - 1];
+        if (m == j) continue;
+        for (int i = 1; i <= n; ++i) std::swap(V(j, i), V(m, i));
+    }
+}
+
 }  // namespace gso

@@ -43,6 +43,8 @@ def lib():
         L.gso_residuals.argtypes = [ci, ci, vp, cl, vp, cl, vp, cl, vp]
         L.gso_hessenberg.argtypes = [ci, ci, vp, cl, vp, vp, cl]
         L.gso_gschur_hess.argtypes = [ci, ci, vp, cl, vp, cl, vp, ci, ci]
+        L.gso_balance.argtypes = [ci, ci, vp, cl, ci, ci, vp, vp, vp]
+        L.gso_balance_apply.argtypes = [ci, ci, vp, cl, vp, vp, vp, ci]
         L.gso_eigvalscond.argtypes = [ci, ci, vp, cl, vp]
         L.gso_gs2x2.argtypes = [vp, vp, vp]
         L.gso_reflector.argtypes = [ci, ci, vp, vp]
@@ -137,6 +139,30 @@ def eigvalscond(T, kind):
     rc = lib().gso_eigvalscond(kind, n, _ptr(T), n, _ptr(s))
     assert rc == 0
     return s
+
+
+def balance(A, scale=True, permute=True):
+    """balance!(A) -> (Abal, D, sp, (ilo, ihi, trivial), rc)   (src/balance.jl:33-199); Float64 / ComplexF64"""
+    kind = 1 if np.iscomplexobj(A) else 0
+    Ab = _prep(A, kind)
+    n = Ab.shape[-1]
+    D = np.zeros(n)
+    sp = np.zeros(n, dtype=np.int32)
+    ii = np.zeros(3, dtype=np.int32)
+    rc = lib().gso_balance(kind, n, _ptr(Ab), n, int(scale), int(permute), _ptr(D), _ptr(sp), _ptr(ii))
+    return Ab, D, sp, (int(ii[0]), int(ii[1]), bool(ii[2])), rc
+
+
+def balance_apply(V, D, sp, ii, inverse=False):
+    """lmul!(B, V) / ldiv!(B, V)   (src/balance.jl:203-260)"""
+    kind = 1 if np.iscomplexobj(V) else 0
+    Vb = _prep(V, kind)
+    n = Vb.shape[-1]
+    iia = np.array([ii[0], ii[1], int(ii[2])], dtype=np.int32)
+    rc = lib().gso_balance_apply(kind, n, _ptr(Vb), n, _ptr(np.ascontiguousarray(D, dtype=np.float64)),
+                                 _ptr(np.ascontiguousarray(sp, dtype=np.int32)), _ptr(iia), int(inverse))
+    assert rc == 0
+    return Vb
 
 
 def gs2x2(a, b, c, d):

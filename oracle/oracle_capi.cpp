@@ -329,6 +329,23 @@ int gso_gschur_batched(int kind, int n, long batch, void* A, void* Z, void* w, i
     return bad.load();
 }
 
+// balance!(A; scale, permute): A in place; D (n doubles), sp (n ints), ii = (ilo, ihi, trivial); kinds 0 and 1
+int gso_balance(int kind, int n, void* A, long lda, int scale, int permute, double* D, int* sp, int* ii) {
+    int ilo = 1, ihi = n, rc = -1;
+    bool trivial = true;
+    if (kind == 0) rc = balance<double>(Mat<double>((double*)A, n, n, lda), scale != 0, permute != 0, D, sp, ilo, ihi, trivial);
+    else if (kind == 1) rc = balance<Cx<double>>(Mat<Cx<double>>((Cx<double>*)A, n, n, lda), scale != 0, permute != 0, D, sp, ilo, ihi, trivial);
+    ii[0] = ilo; ii[1] = ihi; ii[2] = trivial ? 1 : 0;
+    return rc;
+}
+// lmul!(B, V) / ldiv!(B, V)
+int gso_balance_apply(int kind, int n, void* V, long ldv, const double* D, const int* sp, const int* ii, int inv) {
+    if (kind == 0) balance_apply<double>(Mat<double>((double*)V, n, n, ldv), D, sp, ii[0], ii[1], ii[2] != 0, inv != 0);
+    else if (kind == 1) balance_apply<Cx<double>>(Mat<Cx<double>>((Cx<double>*)V, n, n, ldv), D, sp, ii[0], ii[1], ii[2] != 0, inv != 0);
+    else return -1;
+    return 0;
+}
+
 int gso_version(void) { return 1; }
 
 }  // extern "C"
