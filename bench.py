@@ -424,6 +424,34 @@ def measure_workload(gs, torch, dist, args, name, world, rank, local_rank, with_
         e2e = {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * e2e_s, "steps": args.e2e_steps, "stat": "median", "ms_steps": [round(1e3 * t, 1) for t in times],
                "api": "genericschur_jl_b200.gschur_ (pinned host arrays)", "checksum": checksum}
+        # copy-only baseline: the same bytes (A in; T, Z out) through cudaMemcpyAsync on two streams, no kernels — the PCIe /
+        # host-memory ceiling of the end-to-end figure (all ranks at once: at 8 GPUs the host side is the limit)
+        try:
+            s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+            d_in = torch.empty((batch, n, n), dtype=tdt, device="cuda")
+            d_o = torch.empty((batch, n, n), dtype=tdt, device="cuda")
+            ctimes = []
+            for it in range(3):
+                barrier()
+                t0 = time.perf_counter()
+                with torch.cuda.stream(s_in):
+                    d_in.copy_(Ah, non_blocking=True)
+                with torch.cuda.stream(s_out):
+                    Zh.copy_(d_o, non_blocking=True)      # stands for T out
+                    Zh.copy_(d_o, non_blocking=True)      # stands for Z out
+                torch.cuda.synchronize()
+                ctimes.append(time.perf_counter() - t0)
+            c_s = float(min(ctimes[1:]))
+            if world > 1:
+                t = torch.tensor([c_s], dtype=torch.float64, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                c_s = float(t.item())
+            e2e["copy_only"] = {"ms_per_step": 1e3 * c_s, "h2d_GBs_per_gpu": h2d / c_s / 1e9, "d2h_GBs_per_gpu": 2 * batch * n * n * esz / c_s / 1e9,
+                                "value_if_compute_were_free": total / c_s,
+                                "note": "H2D of A and D2H of 2 x (n x n x batch) concurrently on two streams, pinned buffers, all ranks at once"}
+            del d_in, d_o
+        except Exception as exc:      # informational
+            e2e["copy_only"] = {"error": str(exc)}
         del Ah, Zh
         if with_pageable:
             # the drop-in caller's arrays are pageable (a Julia Array): same call on ordinary host memory

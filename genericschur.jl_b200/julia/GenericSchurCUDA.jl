@@ -222,6 +222,51 @@ function hessenberg_cuda!(A::Matrix{T}) where {T}
     return Hessenberg(A, τ), Q
 end
 
+# ---- SURVEY.md section 8(f) ranks 2 and 3: eigenvectors from the Schur form, balancing, triangularize ------------------
+# geigvecs(S; left) (src/vectors.jl:12-20) for ComplexF64 Schur decompositions; other element types keep the package's method
+function GenericSchur.geigvecs(S::Schur{ComplexF64, Matrix{ComplexF64}}; left::Bool = false)
+    n = size(S.T, 1)
+    n <= 128 || return invoke(GenericSchur.geigvecs, Tuple{Schur{T}} where {T}, S; left = left)
+    V = Matrix{ComplexF64}(undef, n, n)
+    haveZ = size(S.Z, 1) > 0
+    rc = ccall((:gschur_cuda_eigvecs_batched, libgschur), Cint,
+        (Cint, Cint, Int64, Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Cint, Int64, Ptr{Cvoid}, Cint, Int64, Cint, UInt32),
+        GSCHUR_C64, n, 1, S.T, n, n * n, haveZ ? pointer(S.Z) : C_NULL, n, n * n, V, n, n * n, left, 0)
+    rc == 0 || error("libgschur_cuda error $rc: " * unsafe_string(ccall((:gschur_cuda_eigvecs_last_error, libgschur), Cstring, ())))
+    return V
+end
+
+# balance!(A; scale, permute) => (Abal, B::Balancer) (src/balance.jl:33-199); the p / algo keywords go to the package's method
+function GenericSchur.balance!(A::Matrix{T}; scale = true, permute = true, kwargs...) where {T <: Union{Float64, ComplexF64}}
+    isempty(kwargs) || return invoke(GenericSchur.balance!, Tuple{AbstractMatrix{T}}, A; scale = scale, permute = permute, kwargs...)
+    n = LinearAlgebra.checksquare(A)
+    D = Vector{Float64}(undef, n)
+    ii = zeros(Int32, 3)
+    sp = zeros(Int32, n)
+    info = zeros(Int32, 1)
+    rc = ccall((:gschur_cuda_balance_batched, libgschur), Cint,
+        (Cint, Cint, Int64, Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Cint, Cint, UInt32),
+        _kind(T), n, 1, A, n, n * n, D, ii, sp, info, scale, permute, 0)
+    rc == 0 || error("libgschur_cuda error $rc")
+    info[1] == 0 || error("NaN encountered while balancing")
+    ilo, ihi = Int(ii[1]), Int(ii[2])
+    B = GenericSchur.Balancer{T}(ilo, ihi, Int.(sp[1:(ilo - 1)]), Int.(sp[(ihi + 1):n]), T.(D), ii[3] != 0)
+    return A, B
+end
+
+# triangularize(S::Schur{Float64}) (src/triang.jl:9-43)
+function GenericSchur.triangularize(S::Schur{Float64, Matrix{Float64}})
+    n = size(S.T, 1)
+    Tc = Matrix{ComplexF64}(undef, n, n)
+    Zc = Matrix{ComplexF64}(undef, n, n)
+    w = Vector{ComplexF64}(undef, n)
+    rc = ccall((:gschur_cuda_triangularize_batched, libgschur), Cint,
+        (Cint, Int64, Ptr{Float64}, Cint, Int64, Ptr{Float64}, Cint, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, UInt32),
+        n, 1, S.T, n, n * n, S.Z, n, n * n, Tc, Zc, w, 0)
+    rc == 0 || error("libgschur_cuda error $rc")
+    return Schur(Tc, Zc, w)
+end
+
 release_workspace() = ccall((:gschur_cuda_release_workspace, libgschur), Cint, ())
 
 end # module
