@@ -24,6 +24,7 @@
 #include <cstdlib>
 #include <type_traits>
 #include "gehrd.cuh"
+#include "gehrd_reg.cuh"
 
 namespace gs {
 
@@ -450,6 +451,14 @@ template <class T, int NMAX> int launch_gehrd_split(const BatchedParams& p, int 
 // kernel's shuffle / predicate overhead outweighs the shorter chains (64x64: 7 ms vs 10 ms), so Float64 keeps the
 // thread-per-column kernel.  GSCHUR_GEHRD=v1|v2 forces one or the other (profiling knob).
 template <class T> int launch_stage_a(const BatchedParams& p, int dev_sms, cudaStream_t stream, std::string* err) {
+    if constexpr (std::is_same<T, double>::value) {
+        // Float64, n <= 64: the register-tiled kernel (gehrd_reg.cuh); GSCHUR_GEHRD=v1 / v2 force the older kernels
+        const char* force = std::getenv("GSCHUR_GEHRD");
+        if (!(force && force[0] == 'v') && p.mode == MODE_SCHUR) {
+            if (p.n <= 32) return launch_gehrd_reg<32>(p, dev_sms, stream, err);
+            if (p.n <= 64) return launch_gehrd_reg<64>(p, dev_sms, stream, err);
+        }
+    }
     if constexpr (std::is_same<T, double>::value || std::is_same<T, cx<double>>::value) {
         const char* force = std::getenv("GSCHUR_GEHRD");
         bool split = std::is_same<T, cx<double>>::value;
