@@ -47,7 +47,7 @@ template <int LPM, int CPL> struct ChainC {
     int istart, iend, its, it, maxiter, maxinner, info;
     bool alive;
 #ifdef GS_QR_PROFILE
-    long long prof_loop;
+    long long prof_loop, prof_ns;
 #endif
 
     __host__ __device__ static int colbase(int j) { return ((j - 1) * (j + 2 * EX)) / 2; }
@@ -538,7 +538,7 @@ template <int LPM, int CPL> struct ChainR {
     int istart, iend, iterqr, it, iwcur, maxiter, info;
     bool alive;
 #ifdef GS_QR_PROFILE
-    long long prof_loop;
+    long long prof_loop, prof_ns;
 #endif
 
     __host__ __device__ static int colbase(int j) { return ((j - 1) * (j + 2 * EX)) / 2; }

@@ -294,13 +294,20 @@ template <int CPL> struct OwnR : ChainR<32, CPL> {
     GS_DEV void run() {
 #ifdef GS_QR_PROFILE
         this->prof_loop = 0;
+        this->prof_ns = 0;
         const long long tr0 = clock64();
 #endif
         for (;;) {
             R r1r = 0, r1i = 0, r2r = 0, r2i = 0;
             bool want = false;
+#ifdef GS_QR_PROFILE
+            const long long tn0 = clock64();
+#endif
             if (this->alive) want = this->next_sweep(r1r, r1i, r2r, r2i);
             __syncwarp();
+#ifdef GS_QR_PROFILE
+            this->prof_ns += clock64() - tn0;
+#endif
             if (!want) break;
             sweep(want, r1r, r1i, r2r, r2i);
             if (this->lg.ovf) {
@@ -311,7 +318,7 @@ template <int CPL> struct OwnR : ChainR<32, CPL> {
         this->st[3] = (unsigned)this->it;
 #ifdef GS_QR_PROFILE
         this->st[0] = (unsigned)((clock64() - tr0) >> 6);
-        this->st[2] = 0u;
+        this->st[2] = (unsigned)(this->prof_ns >> 6);
         this->st[3] = (unsigned)(this->prof_loop >> 6);
 #endif
     }
@@ -592,13 +599,20 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
     GS_DEV void run() {
 #ifdef GS_QR_PROFILE
         this->prof_loop = 0;
+        this->prof_ns = 0;
         const long long tr0 = clock64();
 #endif
         for (;;) {
             C shift = mk_cx<R>(0.0, 0.0);
             bool want = false;
+#ifdef GS_QR_PROFILE
+            const long long tn0 = clock64();
+#endif
             if (this->alive) want = this->next_sweep(shift);
             __syncwarp();
+#ifdef GS_QR_PROFILE
+            this->prof_ns += clock64() - tn0;
+#endif
             if (!want) break;
             sweep(want, shift);
             this->its += 1;
@@ -610,7 +624,7 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
         this->st[3] = (unsigned)this->it;
 #ifdef GS_QR_PROFILE
         this->st[0] = (unsigned)((clock64() - tr0) >> 6);
-        this->st[2] = 0u;
+        this->st[2] = (unsigned)(this->prof_ns >> 6);
         this->st[3] = (unsigned)(this->prof_loop >> 6);
 #endif
     }

@@ -62,7 +62,7 @@ template <class R> struct LogWriter {
         next = p.log_next;
         npages = p.log_pages;
         maxp = p.log_maxp;
-        row = (p.log_table && enable) ? p.log_table + b * (long long)(2 + p.log_maxp) : nullptr;
+        row = p.log_table ? p.log_table + b * (long long)(2 + p.log_maxp) : nullptr;   // a disabled log still reports "no records"
         cur = nullptr;
         left = 0;
         nrec = 0;
