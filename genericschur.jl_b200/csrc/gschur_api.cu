@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <atomic>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -183,7 +184,93 @@ struct ChunkBuf {
     cudaEvent_t evH2D = nullptr, evComp = nullptr, evD2H = nullptr;   // this buffer's chunk: input landed / kernels done / results out
     bool busy = false;                                                 // evD2H has been recorded in this call
     size_t capA = 0, capZ = 0, capw = 0, captau = 0, capn = 0, capst = 0;
+    // pageable caller arrays: pinned staging for this buffer's chunk (A in / T out, Z) and the chunk waiting in it
+    char *hA = nullptr, *hZ = nullptr;
+    size_t hcapA = 0, hcapZ = 0;
+    int64_t pend_c0 = 0, pend_cn = 0;
 };
+
+// A few host threads that copy between pageable caller memory and pinned staging (one memcpy thread moves 6-10 GB/s; the
+// PCIe link takes 55).  The workers are created on first use and live for the life of the process (detached: nothing to
+// join when the library is unloaded at exit).
+class CopyPool {
+public:
+    static CopyPool& get() {
+        static CopyPool* pool = new CopyPool();
+        return *pool;
+    }
+    void copy(char* dst, const char* src, size_t bytes) {
+        if (bytes == 0) return;
+        if (workers_ == 0 || bytes < 4 * kSeg) {
+            std::memcpy(dst, src, bytes);
+            return;
+        }
+        std::lock_guard<std::mutex> job(job_mu_);   // one copy at a time (callers on several devices take turns)
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            dst_ = dst;
+            src_ = src;
+            bytes_ = bytes;
+            next_.store(0);
+            active_ = workers_;
+            gen_ += 1;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [&] { return active_ == 0; });
+    }
+
+private:
+    static constexpr size_t kSeg = (size_t)2 << 20;
+    CopyPool() {
+        int nt = 8;
+        if (const char* e = std::getenv("GSCHUR_COPY_THREADS")) nt = std::atoi(e);
+        const int hc = (int)std::thread::hardware_concurrency();
+        if (hc > 0 && nt > hc) nt = hc;
+        if (nt < 1) nt = 1;
+        workers_ = nt - 1;   // the calling thread copies too
+        for (int i = 0; i < workers_; ++i) std::thread([this] { loop(); }).detach();
+    }
+    void work() {
+        for (;;) {
+            const size_t o = next_.fetch_add(kSeg);
+            if (o >= bytes_) break;
+            std::memcpy(dst_ + o, src_ + o, bytes_ - o < kSeg ? bytes_ - o : kSeg);
+        }
+    }
+    void loop() {
+        unsigned long long seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+            }
+            work();
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--active_ == 0) done_.notify_all();
+        }
+    }
+    std::mutex job_mu_, mu_;
+    std::condition_variable cv_, done_;
+    char* dst_ = nullptr;
+    const char* src_ = nullptr;
+    size_t bytes_ = 0;
+    std::atomic<size_t> next_{0};
+    int workers_ = 0, active_ = 0;
+    unsigned long long gen_ = 0;
+};
+
+cudaError_t grow_pinned(char*& p, size_t& cap, size_t need) {
+    if (need <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaHostAlloc((void**)&p, need, cudaHostAllocDefault);
+    if (e == cudaSuccess) cap = need;
+    return e;
+}
 
 // Per-device staging buffers and streams are cached across calls (grow-only): cudaMalloc / cudaFree of gigabytes
 // and stream creation would otherwise sit inside every end-to-end call.
@@ -268,6 +355,38 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
     const bool zin = wantZ && (J.flags & GSCHUR_FLAG_HESS_INPUT) && !hess;
     const bool denseA = (J.lda == n) && (J.strideA == (int64_t)n * n);
     const bool denseZ = (J.ldz == n) && (J.strideZ == (int64_t)n * n);
+    // Pageable caller memory (a Julia Array, an ordinary numpy array): cudaMemcpyAsync from / to it is staged by the driver
+    // through one thread and synchronous with respect to the host, which serialises the three-stream pipeline (measured:
+    // 52 k instead of 179 k matrices/s on 65536 x 64x64 ComplexF64).  Such slices go through the library's own pinned
+    // staging, filled and drained by the copy pool, chunk by chunk around the device pipeline.  GSCHUR_HOST_STAGING=0: off.
+    bool staged = false;
+    {
+        const char* hs = std::getenv("GSCHUR_HOST_STAGING");
+        const char* hr = std::getenv("GSCHUR_HOST_REGISTER");
+        const bool allowed = !(hs && hs[0] == '0') && !(hr && hr[0] == '1');
+        if (allowed && denseA && (!wantZ || denseZ) && (size_t)count * mat >= ((size_t)8 << 20)) {
+            auto pageable = [&](const char* ptr) {
+                cudaPointerAttributes at;
+                if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+                    cudaGetLastError();
+                    return false;
+                }
+                return at.type == cudaMemoryTypeUnregistered;
+            };
+            staged = pageable(J.A + (size_t)b0 * mat) || (wantZ && pageable(J.Z + (size_t)b0 * mat));
+        }
+        if (staged) {
+            // pinned staging of the NBUF chunks: GSCHUR_STAGE_BUDGET_MB (default 4 GiB)
+            size_t budget = (size_t)4 << 30;
+            if (const char* e = std::getenv("GSCHUR_STAGE_BUDGET_MB")) {
+                const long long v = std::atoll(e);
+                if (v >= 1) budget = (size_t)v << 20;
+            }
+            int64_t fit = (int64_t)(budget / ((size_t)NBUF * (wantZ ? 2 : 1) * mat));
+            if (fit < 1) fit = 1;
+            if (chunk > fit) chunk = fit;
+        }
+    }
     if (cudaSetDevice(dev) != cudaSuccess) {
         *err = "cudaSetDevice failed";
         return GSCHUR_ERR_CUDA;
@@ -342,6 +461,10 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
         if (hess) SL_TRY(grow(buf[i].dtau, buf[i].captau, es * (n > 1 ? n - 1 : 1) * chunk));
         SL_TRY(grow(buf[i].dinfo, buf[i].capn, sizeof(int32_t) * chunk));
         SL_TRY(grow(buf[i].dstats, buf[i].capst, sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX * chunk));
+        if (staged) {
+            SL_TRY(grow_pinned(buf[i].hA, buf[i].hcapA, mat * chunk));
+            if (wantZ) SL_TRY(grow_pinned(buf[i].hZ, buf[i].hcapZ, mat * chunk));
+        }
     }
     {
         // Chunk schedule: full chunks in the middle, a quarter and a half chunk at either end — the first H2D and the last
@@ -366,6 +489,13 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
             }
         }
         int64_t c0 = b0;
+        auto drain = [&](ChunkBuf& B) {
+            if (B.pend_cn <= 0) return;
+            CopyPool::get().copy(J.A + (size_t)B.pend_c0 * mat, B.hA, mat * (size_t)B.pend_cn);
+            if (wantZ) CopyPool::get().copy(J.Z + (size_t)B.pend_c0 * mat, B.hZ, mat * (size_t)B.pend_cn);
+            B.pend_cn = 0;
+        };
+        for (int i = 0; i < NBUF; ++i) buf[i].pend_cn = 0;
         if (trace) {
             cudaEventCreate(&tevK0);
             cudaEventCreate(&tevK1);
@@ -377,8 +507,22 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
             const int64_t cn = sizes[ci];
             cudaStream_t s = P.sH2D;
             // H2D (after the previous chunk in this buffer has been copied out)
-            if (B.busy) SL_TRY(cudaStreamWaitEvent(P.sH2D, B.evD2H, 0));
-            if (denseA) {
+            if (staged) {
+                if (B.busy) {   // the results of the chunk that used this buffer: staging -> caller
+                    SL_TRY(cudaEventSynchronize(B.evD2H));
+                    drain(B);
+                }
+                CopyPool::get().copy(B.hA, J.A + (size_t)c0 * mat, mat * cn);
+                if (zin) CopyPool::get().copy(B.hZ, J.Z + (size_t)c0 * mat, mat * cn);
+                SL_TRY(cudaMemcpyAsync(B.dA, B.hA, mat * cn, cudaMemcpyHostToDevice, s));
+                if (zin) SL_TRY(cudaMemcpyAsync(B.dZ, B.hZ, mat * cn, cudaMemcpyHostToDevice, s));
+                B.pend_c0 = c0;
+                B.pend_cn = cn;
+            } else if (B.busy) {
+                SL_TRY(cudaStreamWaitEvent(P.sH2D, B.evD2H, 0));
+            }
+            if (staged) {
+            } else if (denseA) {
                 SL_TRY(cudaMemcpyAsync(B.dA, J.A + (size_t)c0 * J.strideA * es, mat * cn, cudaMemcpyHostToDevice, s));
             } else {
                 for (int64_t b = 0; b < cn; ++b)
@@ -386,7 +530,7 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
                                              J.A + (size_t)(c0 + b) * J.strideA * es, (size_t)J.lda * es,
                                              (size_t)n * es, n, cudaMemcpyHostToDevice, s));
             }
-            if (zin) {
+            if (zin && !staged) {
                 if (denseZ) {
                     SL_TRY(cudaMemcpyAsync(B.dZ, J.Z + (size_t)c0 * J.strideZ * es, mat * cn, cudaMemcpyHostToDevice, s));
                 } else {
@@ -411,7 +555,10 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
             SL_TRY(cudaEventRecord(B.evComp, P.sComp));
             s = P.sD2H;
             SL_TRY(cudaStreamWaitEvent(P.sD2H, B.evComp, 0));
-            if (denseA) {
+            if (staged) {
+                SL_TRY(cudaMemcpyAsync(B.hA, B.dA, mat * cn, cudaMemcpyDeviceToHost, s));
+                if (wantZ) SL_TRY(cudaMemcpyAsync(B.hZ, B.dZ, mat * cn, cudaMemcpyDeviceToHost, s));
+            } else if (denseA) {
                 SL_TRY(cudaMemcpyAsync(J.A + (size_t)c0 * J.strideA * es, B.dA, mat * cn, cudaMemcpyDeviceToHost, s));
             } else {
                 for (int64_t b = 0; b < cn; ++b)
@@ -419,7 +566,7 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
                                              (char*)B.dA + b * mat, (size_t)n * es, (size_t)n * es, n,
                                              cudaMemcpyDeviceToHost, s));
             }
-            if (wantZ) {
+            if (wantZ && !staged) {
                 if (denseZ) {
                     SL_TRY(cudaMemcpyAsync(J.Z + (size_t)c0 * J.strideZ * es, B.dZ, mat * cn, cudaMemcpyDeviceToHost, s));
                 } else {
@@ -447,6 +594,14 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
             cudaEventRecord(tevK1, P.sComp);
             cudaEventRecord(tevD1, P.sD2H);
             t_enq = now_s();
+        }
+        if (staged) {   // the chunks still in the staging buffers, oldest first
+            const int nc = (int)sizes.size();
+            for (int ci = nc > NBUF ? nc - NBUF : 0; ci < nc; ++ci) {
+                ChunkBuf& B = buf[ci % NBUF];
+                SL_TRY(cudaEventSynchronize(B.evD2H));
+                drain(B);
+            }
         }
     }
 cleanup:
@@ -572,6 +727,7 @@ int gschur_cuda_release_workspace(void) {
         DevicePipe& P = g_pipe[d];
         std::lock_guard<std::mutex> lk(P.mu);
         bool any = P.hstage != nullptr;
+        for (int i = 0; i < NBUF; ++i) any = any || P.buf[i].hA || P.buf[i].hZ;
         for (int i = 0; i < NBUF; ++i) any = any || P.buf[i].dA || P.buf[i].dZ || P.buf[i].dw || P.buf[i].dtau || P.buf[i].dinfo || P.buf[i].dstats;
         if (cudaSetDevice(d) != cudaSuccess) continue;
         if (any) {
@@ -588,6 +744,10 @@ int gschur_cuda_release_workspace(void) {
                 B.dinfo = nullptr;
                 B.dstats = nullptr;
                 B.capA = B.capZ = B.capw = B.captau = B.capn = B.capst = 0;
+                if (B.hA) cudaFreeHost(B.hA);
+                if (B.hZ) cudaFreeHost(B.hZ);
+                B.hA = B.hZ = nullptr;
+                B.hcapA = B.hcapZ = 0;
             }
             if (P.hstage) cudaFreeHost(P.hstage);
             P.hstage = nullptr;
