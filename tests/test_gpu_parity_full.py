@@ -349,3 +349,26 @@ def test_pipeline_budget_and_release(gs, O, monkeypatch):
     assert np.array_equal(S0.T, S2.T) and np.array_equal(S0.Z, S2.Z)
     for b in (0, batch - 1):
         _check_one(O, A[:, :, b], S1.T[:, :, b], S1.Z[:, :, b], S1.values[:, b], 0, 10, f"budget[{b}]")
+
+
+def test_pageable_staging_matches_direct_path(gs, O, monkeypatch):
+    """Ordinary (pageable) arrays go through the library's pinned staging and copy threads: same bytes out as the direct
+    path — Schur with Z, eigenvalues only, Hessenberg factors, and with more chunks than staging buffers."""
+    rng = np.random.default_rng(44)
+    n, batch = 32, 5000
+    A = np.asfortranarray(rng.random((n, n, batch)) + 1j * rng.random((n, n, batch)))
+    monkeypatch.setenv("GSCHUR_HOST_STAGING", "0")
+    S0 = gs.gschur(A)
+    w0 = gs.eigvals(A)
+    H0 = gs.hessenberg(A)
+    monkeypatch.delenv("GSCHUR_HOST_STAGING")
+    for budget in (None, "2"):                              # 2 MiB of staging: ~15 matrices per chunk, hundreds of chunks
+        if budget:
+            monkeypatch.setenv("GSCHUR_STAGE_BUDGET_MB", budget)
+        S1 = gs.gschur(A)
+        assert np.array_equal(S0.T, S1.T) and np.array_equal(S0.Z, S1.Z) and np.array_equal(S0.values, S1.values)
+        assert np.array_equal(w0, gs.eigvals(A))
+        H1 = gs.hessenberg(A)
+        assert np.array_equal(H0.factors, H1.factors) and np.array_equal(H0.tau, H1.tau) and np.array_equal(H0.Q, H1.Q)
+    for b in (0, batch - 1):
+        _check_one(O, A[:, :, b], S1.T[:, :, b], S1.Z[:, :, b], S1.values[:, b], gs.C64, 10, f"staged[{b}]")
