@@ -17,6 +17,18 @@ using namespace gs;
 namespace {
 thread_local std::string l_err;
 }
+// The stream-ordered scratch of the large-matrix path (and of the batched kernels it calls for small blocks and shifts:
+// hundreds of calls per matrix) stays in the device's default pool across synchronisations instead of going back to the
+// driver at each of them.
+static void keep_default_pool() {
+    int d = 0;
+    cudaMemPool_t mp = nullptr;
+    if (cudaGetDevice(&d) == cudaSuccess && cudaDeviceGetDefaultMemPool(&mp, d) == cudaSuccess && mp) {
+        unsigned long long thr = ~0ULL;
+        cudaMemPoolSetAttribute(mp, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+}
+
 extern "C" const char* gschur_cuda_large_last_error(void) { return l_err.c_str(); }
 
 #define L_TRY(expr)                                                              \
@@ -41,6 +53,7 @@ extern "C" int gschur_cuda_hessenberg_large(int n, double* A, int lda, double* t
         return GSCHUR_ERR_CUDA;
     }
     cudaStream_t s = 0;
+    keep_default_pool();
     const bool dev = (flags & GSCHUR_FLAG_DEVICE_PTRS) != 0;
     const size_t nn = (size_t)n * n;
     double *dA = nullptr, *dQ = nullptr;
@@ -120,6 +133,7 @@ extern "C" int gschur_cuda_large(int n, double* A, int lda, double* Z, int ldz, 
         return GSCHUR_ERR_CUDA;
     }
     cudaStream_t s = 0;
+    keep_default_pool();
     const bool dev = (flags & GSCHUR_FLAG_DEVICE_PTRS) != 0;
     const size_t nn = (size_t)n * n;
     double *dA = nullptr, *dZ = nullptr, *dw = nullptr;

@@ -26,7 +26,7 @@ namespace gs {
 constexpr int LQ_NB = 12;       // bulges per chain (2 NB shifts per sweep)
 constexpr int LQ_W = 112;       // maximum window order (H window + U in shared memory: 2 x 112 x 113 x 8 B = 198 KB)
 constexpr int LQ_LDW = 113;     // shared-memory leading dimension (odd: conflict-free rows and columns)
-constexpr int LQ_UW = 4;        // warps that apply the reflectors to U (one row of U per lane)
+constexpr int LQ_UW = LQ_NB;    // warps that apply the reflectors to U: one per bulge (reflector), its lanes stride over the rows of U
 constexpr int LQ_MAXC = 4;      // chains of NB bulges in flight per sweep (each on its own SM)
 constexpr int LQ_DELTA = 192;   // column distance between consecutive chains (>= window + steps per window)
 constexpr int LQ_SMALL = 128;   // active blocks up to this order go to the batched kernel
@@ -82,9 +82,11 @@ __global__ void __launch_bounds__(1024) lq_scan_kernel(double* H, int n, int ien
 // Chase the chain through one window.  Bulge b at time tau sits at column p = L + tau - 4 b (1-based); it is active
 // while L <= p <= I-1.  The window is rows/columns wlo..whi of H.  U (wsz x wsz, ld LQ_W, global) receives the
 // accumulated orthogonal factor: H_window <- U' H_window U.
-// Warps 0..NB-1 chase one bulge each (left phase | barrier | right phase | barrier); warps NB..NB+UW-1 apply the
-// step's reflectors to U (their lanes own the rows of U) off the bulge warps' critical path, picking the
-// parameters up from a double-buffered slot in shared memory at the same two barriers.
+// Warps 0..NB-1 chase one bulge each (left phase | barrier | right phase | barrier); warp NB+q applies reflector q of
+// the step to U (all rows, strided over its lanes) off the bulge warps' critical path, picking the parameters up from
+// a double-buffered slot in shared memory at the same two barriers.  (First version: four U warps, one row of U per
+// lane, the 12 reflectors of a step one after the other, and run-time loops in the phases: 138 us per window of 62
+// steps — 4300 cycles per step, the serial bottleneck of the whole large-matrix path.)
 struct lq_refl {
     double tau1, v1, v2;
     int pc, nr;      // window-local column, reflector order (0 = inactive)
@@ -123,6 +125,9 @@ __global__ void __launch_bounds__(32 * (LQ_NB + LQ_UW)) lq_chase_kernel(double* 
         r2r = shifts[4 * b + 2];
         r2i = shifts[4 * b + 3];
     }
+    // A phase touches at most LQ_W columns (rows): LQ_IT strided passes per lane, fully unrolled — all loads of a phase are
+    // issued before the first dependent FMA (a run-time loop serialises 3 loads -> 5 FMAs -> 3 stores per pass).
+    constexpr int LQ_IT = (LQ_W + 31) / 32;
     for (int tau = tau0; tau < tau0 + M; ++tau) {
         lq_refl* slot = slots + (tau & 1) * LQ_NB;
         int p = 0, nr = 0;
@@ -155,12 +160,27 @@ __global__ void __launch_bounds__(32 * (LQ_NB + LQ_UW)) lq_chase_kernel(double* 
                 tau2 = tau1 * v1;
                 tau3 = tau1 * v2;
                 // ---- left phase: rows p..p+nr-1, columns p..whi (disjoint rows across bulges) ----
-                for (int j = p + lane; j <= whi; j += 32) {
-                    const double a = HW(p, j), bb = HW(p + 1, j), c = (nr == 3) ? HW(p + 2, j) : 0.0;
-                    const double ss = a + v1 * bb + v2 * c;
-                    HW(p, j) = a - ss * tau1;
-                    HW(p + 1, j) = bb - ss * tau2;
-                    if (nr == 3) HW(p + 2, j) = c - ss * tau3;
+                {
+                    const bool r3 = nr == 3;
+                    double* hp = &HW(p, p + lane);
+                    const int left = whi - p - lane;          // columns p+lane+32 i with 32 i <= left
+                    double a[LQ_IT], bb[LQ_IT], c[LQ_IT];
+#pragma unroll
+                    for (int i = 0; i < LQ_IT; ++i) {
+                        const bool in = 32 * i <= left;
+                        a[i] = in ? hp[32 * i * LQ_LDW] : 0.0;
+                        bb[i] = in ? hp[32 * i * LQ_LDW + 1] : 0.0;
+                        c[i] = (in && r3) ? hp[32 * i * LQ_LDW + 2] : 0.0;
+                    }
+#pragma unroll
+                    for (int i = 0; i < LQ_IT; ++i) {
+                        const double ss = a[i] + v1 * bb[i] + v2 * c[i];
+                        if (32 * i <= left) {
+                            hp[32 * i * LQ_LDW] = a[i] - ss * tau1;
+                            hp[32 * i * LQ_LDW + 1] = bb[i] - ss * tau2;
+                            if (r3) hp[32 * i * LQ_LDW + 2] = c[i] - ss * tau3;
+                        }
+                    }
                 }
                 if (lane == 0 && p > L) {
                     HW(p, p - 1) = v0;
@@ -180,30 +200,54 @@ __global__ void __launch_bounds__(32 * (LQ_NB + LQ_UW)) lq_chase_kernel(double* 
         if (is_bulge) {
             // ---- right phase: columns p..p+nr-1, rows wlo..min(p+3, I) (disjoint columns across bulges) ----
             if (active) {
+                const bool r3 = nr == 3;
                 const int rmax = (p + 3 < I) ? p + 3 : I;
-                for (int r = wlo + lane; r <= rmax; r += 32) {
-                    const double a = HW(r, p), bb = HW(r, p + 1), c = (nr == 3) ? HW(r, p + 2) : 0.0;
-                    const double ss = a + v1 * bb + v2 * c;
-                    HW(r, p) = a - ss * tau1;
-                    HW(r, p + 1) = bb - ss * tau2;
-                    if (nr == 3) HW(r, p + 2) = c - ss * tau3;
+                double* hp = &HW(wlo + lane, p);
+                const int left = rmax - wlo - lane;           // rows wlo+lane+32 i with 32 i <= left
+                double a[LQ_IT], bb[LQ_IT], c[LQ_IT];
+#pragma unroll
+                for (int i = 0; i < LQ_IT; ++i) {
+                    const bool in = 32 * i <= left;
+                    a[i] = in ? hp[32 * i] : 0.0;
+                    bb[i] = in ? hp[32 * i + LQ_LDW] : 0.0;
+                    c[i] = (in && r3) ? hp[32 * i + 2 * LQ_LDW] : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < LQ_IT; ++i) {
+                    const double ss = a[i] + v1 * bb[i] + v2 * c[i];
+                    if (32 * i <= left) {
+                        hp[32 * i] = a[i] - ss * tau1;
+                        hp[32 * i + LQ_LDW] = bb[i] - ss * tau2;
+                        if (r3) hp[32 * i + 2 * LQ_LDW] = c[i] - ss * tau3;
+                    }
                 }
             }
         } else {
-            // ---- U <- U G for every reflector of this step (disjoint columns: any order) ----
-            const int r = (b - LQ_NB) * 32 + lane;
-            if (r < wsz) {
-#pragma unroll 4
-                for (int q = 0; q < LQ_NB; ++q) {
-                    const int rn = slot[q].nr;
-                    if (rn == 0) continue;
-                    const int pc = slot[q].pc;
-                    const double t1 = slot[q].tau1, w1 = slot[q].v1, w2 = slot[q].v2;
-                    const double a = UW(r, pc), bb = UW(r, pc + 1), c = (rn == 3) ? UW(r, pc + 2) : 0.0;
-                    const double ss = a + w1 * bb + w2 * c;
-                    UW(r, pc) = a - ss * t1;
-                    UW(r, pc + 1) = bb - ss * (t1 * w1);
-                    if (rn == 3) UW(r, pc + 2) = c - ss * (t1 * w2);
+            // ---- U <- U G: warp NB + q applies reflector q of this step to all rows of U (disjoint columns across warps) ----
+            const int q = b - LQ_NB;
+            const int rn = slot[q].nr;
+            if (rn != 0) {
+                const bool r3 = rn == 3;
+                const double t1 = slot[q].tau1, w1 = slot[q].v1, w2 = slot[q].v2;
+                const double t2 = t1 * w1, t3 = t1 * w2;
+                double* up = &UW(lane, slot[q].pc);
+                const int left = wsz - 1 - lane;
+                double a[LQ_IT], bb[LQ_IT], c[LQ_IT];
+#pragma unroll
+                for (int i = 0; i < LQ_IT; ++i) {
+                    const bool in = 32 * i <= left;
+                    a[i] = in ? up[32 * i] : 0.0;
+                    bb[i] = in ? up[32 * i + LQ_LDW] : 0.0;
+                    c[i] = (in && r3) ? up[32 * i + 2 * LQ_LDW] : 0.0;
+                }
+#pragma unroll
+                for (int i = 0; i < LQ_IT; ++i) {
+                    const double ss = a[i] + w1 * bb[i] + w2 * c[i];
+                    if (32 * i <= left) {
+                        up[32 * i] = a[i] - ss * t1;
+                        up[32 * i + LQ_LDW] = bb[i] - ss * t2;
+                        if (r3) up[32 * i + 2 * LQ_LDW] = c[i] - ss * t3;
+                    }
                 }
             }
         }
