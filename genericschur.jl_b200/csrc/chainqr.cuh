@@ -47,7 +47,7 @@ template <int LPM, int CPL> struct ChainC {
     int istart, iend, its, it, maxiter, maxinner, info;
     bool alive;
 #ifdef GS_QR_PROFILE
-    long long prof_loop, prof_ns;
+    long long prof_loop, prof_ns, prof_x[6];
 #endif
 
     __host__ __device__ static int colbase(int j) { return ((j - 1) * (j + 2 * EX)) / 2; }
@@ -115,6 +115,9 @@ template <int LPM, int CPL> struct ChainC {
                 info = iend;
                 return false;
             }
+#ifdef GS_QR_PROFILE
+            const long long tx0 = clock64();
+#endif
             int found = 0;
             for (int base = iend - 1; base >= istart && !found; base -= LPM) {
                 const int c = base - sub;
@@ -126,12 +129,18 @@ template <int LPM, int CPL> struct ChainC {
             ssync();
             if (istart > 1 && sub == 0) stc(istart, istart - 1, mk_cx<R>(0.0, 0.0));
             ssync();
+#ifdef GS_QR_PROFILE
+            prof_x[0] += clock64() - tx0;
+#endif
             if (istart >= iend) {
                 iend -= 1;
                 istart = 1;
                 its = 0;
                 continue;
             }
+#ifdef GS_QR_PROFILE
+            const long long tx1 = clock64();
+#endif
             if (its % 30 == 10) {
                 const R s = 0.75 * fabs(ld(istart + 1, istart).re);
                 t = ld(istart, istart);
@@ -160,6 +169,9 @@ template <int LPM, int CPL> struct ChainC {
                     t = t - u * c_div_q(u, x + y);
                 }
             }
+#ifdef GS_QR_PROFILE
+            prof_x[1] += clock64() - tx1 + (long long)(t.re == 1.2345e300);
+#endif
             st[0] += 1;
             return true;
         }

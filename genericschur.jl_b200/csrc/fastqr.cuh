@@ -476,9 +476,9 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
                 if (jj[s] >= k) {
                     const uint32_t a = ca[s] + kb;
                     const C b = lds_e<T>(a + ES);
-                    const C ss = tau1c * cL[s] + tau2 * b;
+                    const C ss = e_axty<(CPL >= 2)>(tau1c, cL[s], tau2, b);
                     sts_e<T>(a, cL[s] - ss);
-                    cL[s] = b - ss * v2;
+                    cL[s] = e_bsv<(CPL >= 2)>(b, ss, v2);
                     if (jj[s] <= k + 1) sts_e<T>(a + ES, cL[s]);   // diagonal columns publish their carry
                 }
             }
@@ -490,9 +490,9 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
                 if (ii[s] <= jmax) {
                     const C d = (ii[s] >= k) ? lds_e<T>(ak + ib[s]) : dR[s];
                     const C e = lds_e<T>(ak1 + ib[s]);
-                    const C ss = tau1 * d + tau2 * e;
+                    const C ss = e_axty<(CPL >= 2)>(tau1, d, tau2, e);
                     sts_e<T>(ak + ib[s], d - ss);
-                    dR[s] = e - ss * v2c;
+                    dR[s] = e_bsv<(CPL >= 2)>(e, ss, v2c);
                     if (ii[s] >= k + 1) sts_e<T>(ak1 + ib[s], dR[s]);
                 }
             }
@@ -1661,7 +1661,7 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
                                 const R tau2 = tau1.re * v2.re - tau1.im * v2.im;
 #pragma unroll
                                 for (int s = 0; s < CPL; ++s) {
-                                    const C ss = tau1 * z[t][s] + tau2 * z[t + 1][s];
+                                    const C ss = e_axty<(CPL >= 2)>(tau1, z[t][s], tau2, z[t + 1][s]);
                                     z[t][s] = z[t][s] - ss;
                                     z[t + 1][s] = e_fnma(ss, v2c, z[t + 1][s]);
                                 }
@@ -1715,9 +1715,9 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
                                 const int r = lane + 1 + 32 * s;
                                 if (r <= n) {
                                     const C z1 = zn[s];
-                                    const C ss = tau1 * z0[s] + tau2 * z1;
+                                    const C ss = e_axty<(CPL >= 2)>(tau1, z0[s], tau2, z1);
                                     ZZ(r, k) = z0[s] - ss;
-                                    z0[s] = z1 - ss * v2c;
+                                    z0[s] = e_bsv<(CPL >= 2)>(z1, ss, v2c);
                                     zn[s] = zp[s];
                                 }
                             }

@@ -360,6 +360,10 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
             ib[s] = ES * (uint32_t)(valid ? j : 1);
             c[s] = mk_cx<R>(0.0, 0.0);
         }
+#ifdef GS_QR_PROFILE
+        const long long ty0 = clock64();
+        long long ty1 = ty0;
+#endif
         if (want) {
             // ---- start row (src/GenericSchur.jl:390-420) ----
             int istart1 = 0;
@@ -378,6 +382,9 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
                 if (m) istart1 = base - (__ffs(m) - 1);
             }
             if (!istart1) istart1 = istart;
+#ifdef GS_QR_PROFILE
+            ty1 = clock64();
+#endif
             const int k0 = istart1;
             C v0, v1;
             {
@@ -424,6 +431,8 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
         this->ssync();
 #ifdef GS_QR_PROFILE
         const long long tl0 = clock64();
+        this->prof_x[2] += ty1 - ty0;
+        this->prof_x[3] += tl0 - ty1;
 #endif
         int t = 0;
         for (;;) {
@@ -564,7 +573,8 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
             }
         }
 #ifdef GS_QR_PROFILE
-        this->prof_loop += clock64() - tl0;
+        const long long tl1 = clock64();
+        this->prof_loop += tl1 - tl0;
 #endif
         if (want && len > 0) {
             // ---- the far carries are written back after the last step (k = iend-1); the unit-modulus factor that makes
@@ -594,10 +604,14 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
             }
             this->ssync();
         }
+#ifdef GS_QR_PROFILE
+        this->prof_x[4] += clock64() - tl1;
+#endif
     }
 
     GS_DEV void run() {
 #ifdef GS_QR_PROFILE
+        for (int q = 0; q < 6; ++q) this->prof_x[q] = 0;
         this->prof_loop = 0;
         this->prof_ns = 0;
         const long long tr0 = clock64();
@@ -626,6 +640,9 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
         this->st[0] = (unsigned)((clock64() - tr0) >> 6);
         this->st[2] = (unsigned)(this->prof_ns >> 6);
         this->st[3] = (unsigned)(this->prof_loop >> 6);
+        if (this->sub == 0 && blockIdx.x == 5)
+            printf("profile matrix (CTA 5): scan %lld shift %lld | start-row %lld first-reflector %lld epilogue %lld | loops %lld total %lld\n",
+                   this->prof_x[0], this->prof_x[1], this->prof_x[2], this->prof_x[3], this->prof_x[4], this->prof_loop, clock64() - tr0);
 #endif
     }
 };
