@@ -423,9 +423,11 @@ template <class T> StageCKernel stage_c_select(int n) {
             k.smem = zreg_layout<T, 32, 32>::bytes();
         } else {
             constexpr int NREG = CX ? 32 : 64;   // ComplexF64: the leading 32 columns stay in shared memory
-            k.fn = gschur_zreg_kernel<T, 64, NREG, 6>;
+            // ... 32 KB of it: half-page staging buffers (2 x 2 KB) let a sixth CTA onto the SM (registers allow six)
+            constexpr int STG = CX ? LOG_PAGE_REC / 2 : LOG_PAGE_REC;
+            k.fn = gschur_zreg_kernel<T, 64, NREG, 6, STG>;
             k.threads = 64;
-            k.smem = zreg_layout<T, 64, NREG>::bytes();
+            k.smem = zreg_layout<T, 64, NREG, STG>::bytes();
         }
         k.name = "zreg";
         return k;

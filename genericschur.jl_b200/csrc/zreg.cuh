@@ -271,20 +271,26 @@ template <int N> struct ZRegR {
     }
 };
 
-template <class T, int N, int NREG> struct zreg_layout {
+// STG: records per staging buffer (a page, or a fraction of one where the shared memory decides the occupancy)
+template <class T, int N, int NREG, int STG = LOG_PAGE_REC> struct zreg_layout {
     static constexpr int NS = N - NREG;
     static constexpr int PAGE_BYTES = LOG_PAGE_REC * 32;
+    static constexpr int STG_BYTES = STG * 32;
+    static_assert(LOG_PAGE_REC % STG == 0, "a staging buffer holds a whole fraction of a page");
     __host__ __device__ static constexpr size_t off_pages() { return (size_t)NS * N * sizeof(T); }
-    __host__ __device__ static constexpr size_t off_ident() { return off_pages() + 2 * (size_t)PAGE_BYTES; }
+    __host__ __device__ static constexpr size_t off_ident() { return off_pages() + 2 * (size_t)STG_BYTES; }
     __host__ __device__ static constexpr size_t bytes() { return off_ident() + 32; }
 };
 
 // N threads per CTA (one per row, rows >= n idle), one matrix per CTA at a time
-template <class T, int N, int NREG, int MINB> __global__ void __launch_bounds__(N, MINB) gschur_zreg_kernel(BatchedParams p) {
-    typedef zreg_layout<T, N, NREG> ZL;
+template <class T, int N, int NREG, int MINB, int STG = LOG_PAGE_REC>
+__global__ void __launch_bounds__(N, MINB) gschur_zreg_kernel(BatchedParams p) {
+    typedef zreg_layout<T, N, NREG, STG> ZL;
     constexpr bool CX = etraits<T>::is_complex;
     constexpr int NS = ZL::NS;
     constexpr int PB = ZL::PAGE_BYTES;
+    constexpr int SB = ZL::STG_BYTES;
+    constexpr int SPP = LOG_PAGE_REC / STG;   // staging buffers per page
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n;
     const int tid = threadIdx.x;
@@ -297,12 +303,12 @@ template <class T, int N, int NREG, int MINB> __global__ void __launch_bounds__(
         const int* row = p.log_table + b * (long long)(2 + p.log_maxp);
         const int nrec = row[0];
         if (nrec <= 0 || row[1] != 0) continue;      // nothing logged, or the fused kernel redoes this matrix
-        const int npages = (nrec + LOG_PAGE_REC - 1) / LOG_PAGE_REC;
+        const int npages = (nrec + STG - 1) / STG;   // staging buffers to go through
         T* gZ = reinterpret_cast<T*>(p.Z) + b * p.strideZ + (act ? tid : 0);
         auto fetch_page = [&](int pgi) {
-            const unsigned char* src = p.log_pool + (size_t)row[2 + pgi] * PB;
-            const uint32_t dst = pg32 + (uint32_t)((pgi & 1) * PB);
-            for (int o = tid * 16; o < PB; o += N * 16) zr_cp_async16(dst + o, src + o);
+            const unsigned char* src = p.log_pool + (size_t)row[2 + pgi / SPP] * PB + (size_t)(pgi % SPP) * SB;
+            const uint32_t dst = pg32 + (uint32_t)((pgi & 1) * SB);
+            for (int o = tid * 16; o < SB; o += N * 16) zr_cp_async16(dst + o, src + o);
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
         fetch_page(0);
@@ -327,8 +333,8 @@ template <class T, int N, int NREG, int MINB> __global__ void __launch_bounds__(
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                 }
                 __syncthreads();
-                const int cnt = (nrec - pgi * LOG_PAGE_REC < LOG_PAGE_REC) ? nrec - pgi * LOG_PAGE_REC : LOG_PAGE_REC;
-                RP.page(pg32 + (uint32_t)((pgi & 1) * PB), cnt);
+                const int cnt = (nrec - pgi * STG < STG) ? nrec - pgi * STG : STG;
+                RP.page(pg32 + (uint32_t)((pgi & 1) * SB), cnt);
                 __syncthreads();
             }
             if (act) {
@@ -357,8 +363,8 @@ template <class T, int N, int NREG, int MINB> __global__ void __launch_bounds__(
                     asm volatile("cp.async.wait_group 0;" ::: "memory");
                 }
                 __syncthreads();
-                const int cnt = (nrec - pgi * LOG_PAGE_REC < LOG_PAGE_REC) ? nrec - pgi * LOG_PAGE_REC : LOG_PAGE_REC;
-                RP.page(pg32 + (uint32_t)((pgi & 1) * PB), cnt);
+                const int cnt = (nrec - pgi * STG < STG) ? nrec - pgi * STG : STG;
+                RP.page(pg32 + (uint32_t)((pgi & 1) * SB), cnt);
                 __syncthreads();
             }
             if (act) {
