@@ -113,8 +113,28 @@ template <class R> GS_DEV R reflector_real_small_generic(R& v0, R& v1, R& v2, in
     return tau;
 }
 
+// Double-double fast path: the same quantities as the generic routine (beta = -sign(alpha) ||x||, tau = (beta - alpha) /
+// beta, tail / (alpha - beta)) from one reciprocal square root and one reciprocal (scalar.cuh: dd_rsqrt_fast, dd_rcp_fast)
+// instead of a scaled hypot and two divisions; out-of-range input takes the generic routine.
 GS_DEV dd_t reflector_real_small(dd_t& v0, dd_t& v1, dd_t& v2, int nr) {
-    return reflector_real_small_generic<dd_t>(v0, v1, v2, nr);
+    const dd_t zero = mk_dd(0.0);
+    if (nr <= 1) return zero;
+    if (nr == 2) v2 = zero;
+    if (v1 == zero && v2 == zero) return zero;
+    const double w = fmax(fabs(v0.hi), fmax(fabs(v1.hi), fabs(v2.hi)));
+    if (!(w >= 1e-100 && w <= 1e100)) return reflector_real_small_generic<dd_t>(v0, v1, v2, nr);
+    const dd_t alpha = v0;
+    const dd_t q = alpha * alpha + (v1 * v1 + v2 * v2);
+    const dd_t rs = dd_rsqrt_fast(q);
+    const dd_t nrm = q * rs;
+    const bool neg = signbit(alpha.hi);
+    const dd_t beta = neg ? nrm : -nrm, rbeta = neg ? rs : -rs;
+    const dd_t tau = (beta - alpha) * rbeta;
+    const dd_t t = dd_rcp_fast(alpha - beta);
+    v1 = v1 * t;
+    v2 = v2 * t;
+    v0 = beta;
+    return tau;
 }
 // Float64 fast path: same quantities (beta = -sign(alpha) ||x||, tau = (beta - alpha)/beta, tail / (alpha - beta)),
 // computed on a copy scaled by an exact power of two with one fast sqrt and two fast reciprocals.
@@ -167,7 +187,27 @@ template <class R> GS_DEV cx<R> reflector_cplx2_generic(cx<R>& v0, cx<R>& v1) {
     return tau;
 }
 
-GS_DEV cx<dd_t> reflector_cplx2(cx<dd_t>& v0, cx<dd_t>& v1) { return reflector_cplx2_generic<dd_t>(v0, v1); }
+// Complex double-double fast path (see reflector_real_small above): tau = (beta - alpha) / beta, v1 <- v1 / (alpha - beta)
+// with 1 / (alpha - beta) = conj(d) / |d|^2.
+GS_DEV cx<dd_t> reflector_cplx2(cx<dd_t>& v0, cx<dd_t>& v1) {
+    const dd_t zero = mk_dd(0.0);
+    const dd_t ar = v0.re, ai = v0.im;
+    if (v1.re == zero && v1.im == zero && ai == zero) return mk_cx<dd_t>(zero, zero);
+    const double w = fmax(fmax(fabs(ar.hi), fabs(ai.hi)), fmax(fabs(v1.re.hi), fabs(v1.im.hi)));
+    if (!(w >= 1e-100 && w <= 1e100)) return reflector_cplx2_generic<dd_t>(v0, v1);
+    const dd_t q = (ar * ar + ai * ai) + (v1.re * v1.re + v1.im * v1.im);
+    const dd_t rs = dd_rsqrt_fast(q);
+    const dd_t nrm = q * rs;
+    const bool neg = signbit(ar.hi);
+    const dd_t beta = neg ? nrm : -nrm, rbeta = neg ? rs : -rs;
+    const cx<dd_t> tau = mk_cx<dd_t>((beta - ar) * rbeta, -(ai * rbeta));
+    const dd_t dr = ar - beta;
+    const dd_t rm = dd_rcp_fast(dr * dr + ai * ai);
+    const cx<dd_t> t = mk_cx<dd_t>(dr * rm, -(ai * rm));
+    v1 = v1 * t;
+    v0 = mk_cx<dd_t>(beta, zero);
+    return tau;
+}
 GS_DEV cx<double> reflector_cplx2(cx<double>& v0, cx<double>& v1) {
     const double ar = v0.re, ai = v0.im;
     if (v1.re == 0.0 && v1.im == 0.0 && ai == 0.0) return mk_cx<double>(0.0, 0.0);

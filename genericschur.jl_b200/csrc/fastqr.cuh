@@ -194,6 +194,17 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
     static constexpr int EX = CPLX ? 2 : 3;   // rows stored below the diagonal in each packed column
     static constexpr int RB = ring_bufs<T, CPL>::value;  // ring buffers (2 or 3)
     static constexpr int BAR_FULL0 = 1, BAR_EMPTY0 = 1 + RB;
+    // Complex double-double at CPL = 3 (65 <= n <= 96): the three columns / rows a lane owns go to three H-warps — the
+    // driver (slot 0: everything the single H-warp did, for its own slot) and NH - 1 helpers that run the step loop of a
+    // sweep for their slot and are parked at a barrier otherwise (see sweep_steps / helper_loop).
+    static constexpr int NH = (etraits<T>::is_complex && sizeof(R) == 16 && CPL == 3 && !LOG) ? CPL : 1;
+    static constexpr int BAR_HSTEP = 7, BAR_HCMD = 8;
+    struct HCmd {
+        int op, k0, istart, iend;
+        C v0, v1;
+    };
+    enum { HCMD_SWEEP = 1, HCMD_EXIT = 2 };
+    HCmd* hcmd;
     int rbase;                                           // first record of the buffer being filled: (sidx % RB) * cap
     int n, ldz, lane, cap;
     T* H;            // packed upper Hessenberg (+ bulge slots), shared memory
@@ -406,6 +417,129 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
         cnt += 1;
     }
 
+    // ---- barriers among the NH H-warps (a plain __syncwarp when there is one) ----
+    GS_DEV static void hbar() {
+        if constexpr (NH > 1) asm volatile("bar.sync %0, %1;" ::"n"(BAR_HSTEP), "n"(32 * NH) : "memory");
+        else __syncwarp();
+    }
+    GS_DEV static void cbar() {
+        if constexpr (NH > 1) asm volatile("bar.sync %0, %1;" ::"n"(BAR_HCMD), "n"(32 * NH) : "memory");
+    }
+
+    // The step loop of a single-shift sweep (src/GenericSchur.jl:426-482) for ONE slot: column / row j = lane + 1 + 32 slot
+    // of every lane.  All NH warps execute it in lock step — the reflector is formed redundantly by each (same inputs from
+    // shared memory, same result), the shared entries are written by the driver only, the two barriers of a step order the
+    // left update, the right update and the next reflector's inputs exactly as the __syncwarp's of the one-warp loop do.
+    // (one copy of the loop for driver and helpers: `driver` is a warp-uniform run-time flag — two instantiations would
+    // put two copies of the double-double arithmetic into the instruction caches)
+    __device__ __noinline__ unsigned sweep_steps(bool driver, int slot, int k0, int istart, int iend, C v0, C v1) {
+        const R zero = r_const<R>(0.0), one = r_const<R>(1.0);
+        constexpr uint32_t ES = (uint32_t)sizeof(T);
+        const uint32_t hb = smem_u32(H);
+        const int j = lane + 1 + 32 * slot;
+        const bool valid = j <= n;
+        const int jj = valid ? j : -(1 << 28), ii = valid ? j : (1 << 28);
+        const uint32_t ca = hb + ES * (uint32_t)(colbase(valid ? j : 1) - 1), ib = ES * (uint32_t)(valid ? j : 1);
+        uint32_t ak = hb + ES * (uint32_t)(colbase(k0) - 1);   // column k
+        C cL = (jj >= k0) ? lds_e<T>(ca + ES * k0) : mk_cx<R>(zero, zero);   // H[k, j] of the owned column j >= k
+        C dR = (ii < k0) ? lds_e<T>(ak + ib) : mk_cx<R>(zero, zero);         // H[i, k] of the owned row i < k
+        unsigned napplied = 0;
+        for (int k = k0; k <= iend - 1; ++k) {
+            const uint32_t kb = ES * (uint32_t)k;
+            const uint32_t ak1 = ak + ES * (uint32_t)(k + EX);          // column k+1
+            const uint32_t akm = ak - ES * (uint32_t)(k - 1 + EX);      // column k-1
+            if (k > k0) {
+                v0 = lds_e<T>(akm + kb);
+                v1 = lds_e<T>(akm + kb + ES);
+            }
+            const C tau1 = reflector_cplx2(v0, v1);
+            napplied += 1;
+            const C v2 = v1, v2c = cconj(v1), tau1c = cconj(tau1);
+            const R tau2 = (tau1 * v2).re;
+            if (driver) push_refl_c(k, tau1, v2);
+            // ---- left update of rows k, k+1: the owned column j >= k ----
+            if (jj >= k) {
+                const uint32_t a = ca + kb;
+                const C b = lds_e<T>(a + ES);
+                const C ss = e_axty<true>(tau1c, cL, tau2, b);
+                sts_e<T>(a, cL - ss);
+                cL = e_bsv<true>(b, ss, v2);
+                if (jj <= k + 1) sts_e<T>(a + ES, cL);   // diagonal columns publish their carry
+            }
+            hbar();
+            // ---- right update of columns k, k+1: the owned row i <= min(k+2, iend) ----
+            const int jmax = (k + 2 < iend) ? k + 2 : iend;
+            if (ii <= jmax) {
+                const C d = (ii >= k) ? lds_e<T>(ak + ib) : dR;
+                const C e = lds_e<T>(ak1 + ib);
+                const C ss = e_axty<true>(tau1, d, tau2, e);
+                sts_e<T>(ak + ib, d - ss);
+                dR = e_bsv<true>(e, ss, v2c);
+                if (ii >= k + 1) sts_e<T>(ak1 + ib, dR);
+            }
+            if (driver && lane == 0 && k > k0) {
+                sts_e<T>(akm + kb, v0);
+                sts_e<T>(akm + kb + ES, mk_cx<R>(zero, zero));
+            }
+            hbar();
+            // column k+1's running entry H[k+1,k+1] was just rewritten by its own lane as row k+1
+            if (jj == k + 1) cL = dR;
+            ak = ak1;
+            if (k == k0 && k0 > istart) {
+                // late start (src/GenericSchur.jl:461-482): flush the carries, the driver rescales in shared memory, reload
+                if (j >= k + 2 && j <= n) HH(k + 1, j) = cL;
+                if (j <= k) HH(j, k + 1) = dR;
+                hbar();
+                if (driver) {
+                    C t = mk_cx<R>(one, zero) - tau1;
+                    R at = c_abs(t);
+                    t = mk_cx<R>(t.re / at, t.im / at);
+                    const C tc = cconj(t);
+                    if (lane == 0) {
+                        HH(k0 + 1, k0) = HH(k0 + 1, k0) * tc;
+                        if (k0 + 2 <= iend) HH(k0 + 2, k0 + 1) = HH(k0 + 2, k0 + 1) * t;
+                    }
+                    __syncwarp();
+                    for (int q = k0; q <= iend; ++q) {
+                        if (q == k0 + 1) continue;
+                        for (int c = q + 1 + lane; c <= n; c += 32) HH(q, c) = HH(q, c) * t;
+                        for (int r = 1 + lane; r <= q - 1; r += 32) HH(r, q) = HH(r, q) * tc;
+                        __syncwarp();
+                    }
+                    emit_scale_c(k0, k0, tc);
+                    emit_scale_c(k0 + 2, iend, tc);
+                }
+                hbar();
+                cL = (j >= k + 1 && j <= n) ? HH(k + 1, j) : mk_cx<R>(zero, zero);
+                dR = (j < k + 1) ? HH(j, k + 1) : mk_cx<R>(zero, zero);
+            }
+        }
+        // ---- flush the carries left after the last step (k = iend-1) ----
+        if (j >= iend + 1 && j <= n) HH(iend, j) = cL;
+        if (j <= iend - 1) HH(j, iend) = dR;
+        hbar();
+        return napplied;
+    }
+
+    // helpers: wait for the driver's command, run the step loop for the slot, repeat
+    GS_DEV void helper_loop(int slot) {
+        for (;;) {
+            cbar();
+            const int op = hcmd->op;
+            if (op == HCMD_EXIT) break;
+            const int k0 = hcmd->k0, is = hcmd->istart, ie = hcmd->iend;
+            const C v0 = hcmd->v0, v1 = hcmd->v1;
+            sweep_steps(false, slot, k0, is, ie, v0, v1);
+        }
+    }
+    GS_DEV void helpers_exit() {
+        if constexpr (NH > 1) {
+            if (lane == 0) hcmd->op = HCMD_EXIT;
+            __syncwarp();
+            cbar();
+        }
+    }
+
     GS_DEV void sweep_complex(const C& shift, int istart, int iend) {
         const R zero = r_const<R>(0.0), one = r_const<R>(1.0);
         const R ulp = rtraits<R>::eps();
@@ -437,6 +571,22 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
             v1 = mk_cx<R>(h21 / s, zero);
         }
         reserve_ops(iend - k0 + 4);
+        if constexpr (NH > 1) {
+            // several H-warps: hand the sweep to the helpers, run the driver's own slot
+            if (lane == 0) {
+                hcmd->op = HCMD_SWEEP;
+                hcmd->k0 = k0;
+                hcmd->istart = istart;
+                hcmd->iend = iend;
+                hcmd->v0 = v0;
+                hcmd->v1 = v1;
+            }
+            __syncwarp();
+            cbar();
+            stp[1] += sweep_steps(true, 0, k0, istart, iend, v0, v1);
+            tail_fix_c(iend);
+            return;
+        }
         // All shared-memory traffic of the step loop goes through 32-bit byte addresses:
         //   &H(i, j) = hb + ES * (colbase(j) - 1 + i).   jj / ii are the owned column / row (sentinels when > n).
         constexpr uint32_t ES = (uint32_t)sizeof(T);
@@ -550,7 +700,12 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
             if (j <= iend - 1) HH(j, iend) = dR[s];
         }
         __syncwarp();
-        // ---- make the tail sub-diagonal real (src/GenericSchur.jl:486-500) ----
+        tail_fix_c(iend);
+    }
+
+    // make the tail sub-diagonal real (src/GenericSchur.jl:486-500); the H-warp (driver) alone
+    GS_DEV void tail_fix_c(int iend) {
+        const R zero = r_const<R>(0.0);
         C t = HH(iend, iend - 1);
         if (t.im != zero) {
             R rt = c_abs(t);
@@ -1860,7 +2015,8 @@ template <class T, int CPL> struct fast_smem_layout {
     __host__ __device__ static size_t off_hdr(int n) {
         return off_ring(n) + L::up16((size_t)ring_bufs<T, CPL>::value * (size_t)cap(n) * sizeof(ZOp));
     }
-    __host__ __device__ static size_t bytes(int n) { return off_hdr(n) + L::up16(sizeof(zring_hdr)); }
+    __host__ __device__ static size_t off_cmd(int n) { return off_hdr(n) + L::up16(sizeof(zring_hdr)); }
+    __host__ __device__ static size_t bytes(int n) { return off_cmd(n) + (FS::NH > 1 ? L::up16(sizeof(typename FS::HCmd)) : 0); }
 };
 
 // register budget: small real tiles are occupancy-bound (cap at 64 registers -> 16 CTAs/SM), the others shared-memory-bound
@@ -1872,13 +2028,19 @@ template <class T, int CPL> struct qr_min_blocks {
                                  : 1;
 };
 
+// threads per CTA: the H-warp and the Z-warp, plus the helper H-warps of the complex double-double kernel at CPL = 3
+template <class T, int CPL> struct qr_threads {
+    static constexpr int value = 64 + 32 * (FastSolver<T, CPL>::NH - 1);
+};
+
 template <class T, int CPL>
-__global__ void __launch_bounds__(64, qr_min_blocks<T, CPL>::value) gschur_qr_kernel(BatchedParams p) {
+__global__ void __launch_bounds__((qr_threads<T, CPL>::value), (qr_min_blocks<T, CPL>::value)) gschur_qr_kernel(BatchedParams p) {
     typedef typename etraits<T>::real R;
     typedef cx<R> C;
     constexpr bool CPLX = etraits<T>::is_complex;
-    constexpr int NT = 64;
     typedef FastSolver<T, CPL> FS;
+    constexpr int NT = qr_threads<T, CPL>::value;
+    constexpr int NW = NT / 32;
     typedef fast_smem_layout<T, CPL> FL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int n = p.n;
@@ -1901,7 +2063,7 @@ __global__ void __launch_bounds__(64, qr_min_blocks<T, CPL>::value) gschur_qr_ke
             s_w0 = w;
         }
         __syncthreads();
-        warp ^= (int)((s_w0 >> 2) & 1u);   // role index: 0 = H-warp, 1 = Z-warp
+        warp ^= (int)((s_w0 >> 2) & 1u);   // role index: 0 = H-warp, 1 = Z-warp (2, 3: helper H-warps, interchangeable)
     }
 
     FS F;
@@ -1912,6 +2074,7 @@ __global__ void __launch_bounds__(64, qr_min_blocks<T, CPL>::value) gschur_qr_ke
     F.sW = reinterpret_cast<C*>(smem_raw + FL::off_w(n));
     F.ring = reinterpret_cast<typename FS::ZOp*>(smem_raw + FL::off_ring(n));
     F.hdr = reinterpret_cast<zring_hdr*>(smem_raw + FL::off_hdr(n));
+    F.hcmd = reinterpret_cast<typename FS::HCmd*>(smem_raw + FL::off_cmd(n));
     F.wantZ = wantZ;
     F.ldz = p.ldz;
     T* H = F.H;
@@ -1933,7 +2096,7 @@ __global__ void __launch_bounds__(64, qr_min_blocks<T, CPL>::value) gschur_qr_ke
 
         // ---- load the Hessenberg part into packed storage; bulge slots start at zero ----
         int bad = 0;
-        for (int j = 1 + warp; j <= n; j += 2) {
+        for (int j = 1 + warp; j <= n; j += NW) {
             const int cb = FS::colbase(j);
             for (int i = 1 + lane; i <= j + FS::EX; i += 32) {
                 T v = e_zero<T>();
@@ -1954,6 +2117,7 @@ __global__ void __launch_bounds__(64, qr_min_blocks<T, CPL>::value) gschur_qr_ke
                 int rc;
                 if constexpr (CPLX) rc = F.qr_complex(maxiter, st);
                 else rc = F.qr_real(maxiter, st);
+                F.helpers_exit();
                 if (lane == 0) {
                     s_info = rc;
                     s_stats[0] = st[0];
@@ -1961,8 +2125,10 @@ __global__ void __launch_bounds__(64, qr_min_blocks<T, CPL>::value) gschur_qr_ke
                     s_stats[2] = st[2];
                     s_stats[3] = st[3];
                 }
-            } else if (wantZ) {
-                z_consumer_entry<T, CPL>(n, lane, F.ldz, F.Z, F.ring, F.hdr, F.cap);
+            } else if (warp == 1) {
+                if (wantZ) z_consumer_entry<T, CPL>(n, lane, F.ldz, F.Z, F.ring, F.hdr, F.cap);
+            } else {
+                if constexpr (FS::NH > 1) F.helper_loop(warp - 1);
             }
             __syncthreads();
             info = s_info;
@@ -1995,7 +2161,7 @@ __global__ void __launch_bounds__(64, qr_min_blocks<T, CPL>::value) gschur_qr_ke
             __syncthreads();
         }
         // ---- store T (exact zeros below the (quasi-)triangle), w, info, stats ----
-        for (int j = 1 + warp; j <= n; j += 2) {
+        for (int j = 1 + warp; j <= n; j += NW) {
             const int cb = FS::colbase(j);
             for (int i = 1 + lane; i <= n; i += 32) {
                 const bool keep = CPLX ? (i <= j) : (i <= j + 1);
@@ -2051,7 +2217,7 @@ template <class T, int CPL> int launch_fast(const BatchedParams& p_in, int dev_s
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     int per_sm = 0;
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 64, smem);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, qr_threads<T, CPL>::value, smem);
     int rc = 0;
     if (e != cudaSuccess) {
         *err = std::string("qr kernel setup: ") + cudaGetErrorString(e);
@@ -2065,7 +2231,7 @@ template <class T, int CPL> int launch_fast(const BatchedParams& p_in, int dev_s
         long long grid = (long long)per_sm * dev_sms;
         if (grid > p.batch) grid = p.batch;
         if (std::getenv("GSCHUR_QR_FIXED_ROLES")) p.flags |= F_FIXED_ROLES;   // profiling knob
-        kern<<<(unsigned)grid, 64, smem, stream>>>(p);
+        kern<<<(unsigned)grid, qr_threads<T, CPL>::value, smem, stream>>>(p);
         note_launch();
         stage_timing_mark(2, stream);
         e = cudaGetLastError();

@@ -575,7 +575,7 @@ template <class T, int CPL> int launch_fast3(const BatchedParams& p_in, int dev_
         F3_TRY(cudaFuncSetAttribute(kC, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "zreplay kernel setup");
         F3_TRY(cudaFuncSetAttribute(kR, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemR), "qr kernel setup");
         F3_TRY(cudaFuncSetAttribute(kR, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared), "qr kernel setup");
-        F3_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perR, kR, 64, smemR), "qr kernel occupancy");
+        F3_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perR, kR, qr_threads<T, CPL>::value, smemR), "qr kernel occupancy");
         if (perB < 1 || perR < 1) {
             *err = "qr kernels do not fit on an SM";
             rc = -3;
@@ -634,7 +634,7 @@ template <class T, int CPL> int launch_fast3(const BatchedParams& p_in, int dev_
             grid = (long long)perR * dev_sms;
             if (grid > cn) grid = cn;
             if (grid > 2 * dev_sms) grid = 2 * dev_sms;
-            kR<<<(unsigned)grid, 64, smemR, stream>>>(p);
+            kR<<<(unsigned)grid, qr_threads<T, CPL>::value, smemR, stream>>>(p);
             note_launch();
             stage_timing_mark(3, stream);
             F3_TRY(cudaGetLastError(), "three-stage kernel launch");

@@ -201,6 +201,38 @@ GS_DEV void pow2_scales(double w, double& down, double& up) {
 // slow-path branches); outside they fall back to IEEE division / sqrt.  The double-double overloads are the
 // exact operations.
 // ------------------------------------------------------------------------------------------------
+// Double-double reciprocal and reciprocal square root for the reflector on the serial chain of the double-double sweeps:
+// a Float64 seed (MUFU + Newton, ~1 ulp) and ONE Newton step carried out in double-double.  The generic operators cost
+// three IEEE divisions (a / b) resp. an IEEE sqrt and a reciprocal (Karp) in sequence; the six of them in the generic
+// complex reflector were ~10 000 cycles of dependent latency per bulge step.  Operands: finite, normal, in a range whose
+// squares do not leave the Float64 range (the callers guard).  Relative error ~2^-104 (the step's own truncation error is
+// e^3 resp. (3/8) e^2 with e ~ 2^-52).
+GS_DEV dd_t dd_rcp_fast(const dd_t& b) {
+    const double x0 = fast_rcp(b.hi);
+    const dd_t e = mk_dd(1.0) - dd_mul_d(b, x0);          // 1 - b x0 ~ 2^-52
+    const double corr = x0 * fma(e.hi, e.hi, e.hi);        // x0 (e + e^2)
+    double s, t;
+    quick_two_sum(x0, corr, s, t);
+    return mk_dd(s, t);
+}
+GS_DEV dd_t dd_rsqrt_fast(const dd_t& q) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(q.hi));
+    {   // two Float64 Newton steps: 20 -> 40 -> 53 bits
+        double e = fma(-q.hi * y0, y0, 1.0);
+        y0 = fma(y0 * e, fma(e, 0.375, 0.5), y0);
+        e = fma(-q.hi * y0, y0, 1.0);
+        y0 = fma(y0 * e, 0.5, y0);
+    }
+    double p, pe;
+    two_prod(y0, y0, p, pe);                               // y0^2 exactly
+    const dd_t e = mk_dd(1.0) - q * mk_dd(p, pe);          // 1 - q y0^2 ~ 2^-52
+    const double corr = 0.5 * y0 * e.hi;
+    double s, t;
+    quick_two_sum(y0, corr, s, t);
+    return mk_dd(s, t);
+}
+
 GS_DEV bool q_exp_in(double a, unsigned lo, unsigned hi) {   // biased exponent of a in [lo, hi]
     const unsigned e = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
     return (e - lo) <= (hi - lo);
