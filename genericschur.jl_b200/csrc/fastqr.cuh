@@ -79,43 +79,43 @@ template <> struct ring_bufs<double, 1> { static constexpr int value = GS_RING_F
 
 // named barriers with immediate ids (a register id would make ptxas reserve all 16 barriers per CTA):
 // full[b] = 1 + b, empty[b] = 1 + RB + b
-template <int ID> GS_DEV void bar_sync_imm() { asm volatile("bar.sync %0, 64;" ::"n"(ID) : "memory"); }
-template <int ID> GS_DEV void bar_arrive_imm() { asm volatile("bar.arrive %0, 64;" ::"n"(ID) : "memory"); }
-template <int RB> GS_DEV void named_bar_sync(int id) {
+template <int ID, int CNT = 64> GS_DEV void bar_sync_imm() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(CNT) : "memory"); }
+template <int ID, int CNT = 64> GS_DEV void bar_arrive_imm() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(CNT) : "memory"); }
+template <int RB, int CNT = 64> GS_DEV void named_bar_sync(int id) {
     if constexpr (RB == 2) {
         switch (id) {
-            case 1: bar_sync_imm<1>(); break;
-            case 2: bar_sync_imm<2>(); break;
-            case 3: bar_sync_imm<3>(); break;
-            default: bar_sync_imm<4>(); break;
+            case 1: bar_sync_imm<1, CNT>(); break;
+            case 2: bar_sync_imm<2, CNT>(); break;
+            case 3: bar_sync_imm<3, CNT>(); break;
+            default: bar_sync_imm<4, CNT>(); break;
         }
     } else {
         switch (id) {
-            case 1: bar_sync_imm<1>(); break;
-            case 2: bar_sync_imm<2>(); break;
-            case 3: bar_sync_imm<3>(); break;
-            case 4: bar_sync_imm<4>(); break;
-            case 5: bar_sync_imm<5>(); break;
-            default: bar_sync_imm<6>(); break;
+            case 1: bar_sync_imm<1, CNT>(); break;
+            case 2: bar_sync_imm<2, CNT>(); break;
+            case 3: bar_sync_imm<3, CNT>(); break;
+            case 4: bar_sync_imm<4, CNT>(); break;
+            case 5: bar_sync_imm<5, CNT>(); break;
+            default: bar_sync_imm<6, CNT>(); break;
         }
     }
 }
-template <int RB> GS_DEV void named_bar_arrive(int id) {
+template <int RB, int CNT = 64> GS_DEV void named_bar_arrive(int id) {
     if constexpr (RB == 2) {
         switch (id) {
-            case 1: bar_arrive_imm<1>(); break;
-            case 2: bar_arrive_imm<2>(); break;
-            case 3: bar_arrive_imm<3>(); break;
-            default: bar_arrive_imm<4>(); break;
+            case 1: bar_arrive_imm<1, CNT>(); break;
+            case 2: bar_arrive_imm<2, CNT>(); break;
+            case 3: bar_arrive_imm<3, CNT>(); break;
+            default: bar_arrive_imm<4, CNT>(); break;
         }
     } else {
         switch (id) {
-            case 1: bar_arrive_imm<1>(); break;
-            case 2: bar_arrive_imm<2>(); break;
-            case 3: bar_arrive_imm<3>(); break;
-            case 4: bar_arrive_imm<4>(); break;
-            case 5: bar_arrive_imm<5>(); break;
-            default: bar_arrive_imm<6>(); break;
+            case 1: bar_arrive_imm<1, CNT>(); break;
+            case 2: bar_arrive_imm<2, CNT>(); break;
+            case 3: bar_arrive_imm<3, CNT>(); break;
+            case 4: bar_arrive_imm<4, CNT>(); break;
+            case 5: bar_arrive_imm<5, CNT>(); break;
+            default: bar_arrive_imm<6, CNT>(); break;
         }
     }
 }
@@ -198,7 +198,11 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
     // driver (slot 0: everything the single H-warp did, for its own slot) and NH - 1 helpers that run the step loop of a
     // sweep for their slot and are parked at a barrier otherwise (see sweep_steps / helper_loop).
     static constexpr int NH = (etraits<T>::is_complex && sizeof(R) == 16 && CPL == 3 && !LOG) ? CPL : 1;
+    // ... and the three rows of Z a lane owns to NH Z-warps (all of them consume every record of the ring)
+    static constexpr int NZW = NH;
+    static constexpr int RING_THREADS = 32 * (1 + NZW);   // the driver and the Z-warps meet at the ring's named barriers
     static constexpr int BAR_HSTEP = 7, BAR_HCMD = 8;
+    int zslot;
     struct HCmd {
         int op, k0, istart, iend;
         C v0, v1;
@@ -291,7 +295,7 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
 #ifdef GS_QR_PROFILE
         const long long tb0 = clock64();
 #endif
-        if (sidx >= RB) named_bar_sync<RB>(BAR_EMPTY0 + sidx % RB);
+        if (sidx >= RB) named_bar_sync<RB, RING_THREADS>(BAR_EMPTY0 + sidx % RB);
 #ifdef GS_QR_PROFILE
         prof[1] += clock64() - tb0;
 #endif
@@ -306,7 +310,7 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
             hdr->end[b] = end;
         }
         __syncwarp();
-        named_bar_arrive<RB>(BAR_FULL0 + b);
+        named_bar_arrive<RB, RING_THREADS>(BAR_FULL0 + b);
         sidx += 1;
     }
     GS_DEV void ensure_space(int m) {
@@ -372,7 +376,7 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
         publish(1);
         // balance the outstanding "empty" arrivals of the last RB buffers
         const int last = sidx - 1;
-        for (int c = (last - (RB - 1) < 0 ? 0 : last - (RB - 1)); c <= last; ++c) named_bar_sync<RB>(BAR_EMPTY0 + c % RB);
+        for (int c = (last - (RB - 1) < 0 ? 0 : last - (RB - 1)); c <= last; ++c) named_bar_sync<RB, RING_THREADS>(BAR_EMPTY0 + c % RB);
     }
 
     // ================================================================================================
@@ -1780,7 +1784,7 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
         const R zero = r_const<R>(0.0);
         for (int cidx = 0;; ++cidx) {
             const int b = cidx % RB;
-            named_bar_sync<RB>(BAR_FULL0 + b);
+            named_bar_sync<RB, RING_THREADS>(BAR_FULL0 + b);
             const int count = hdr->count[b];
             const int end = hdr->end[b];
             const ZOp* ops = ring + b * cap;
@@ -1842,6 +1846,37 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
                                 if (r <= n) ZZ(r, j) = ZZ(r, j) * t;
                             }
                         }
+                        i += 1;
+                    }
+                } else if constexpr (CPLX && NH > 1) {
+                    // one row per lane: this Z-warp's slot (the other rows belong to the other Z-warps)
+                    const int r = lane + 1 + 32 * zslot;
+                    const bool rv = r <= n;
+                    if (op == ZOP_REFL) {
+                        int k = ops[i].k;
+                        C z0 = rv ? ZZ(r, k) : mk_cx<R>(zero, zero);
+                        C zn = rv ? ZZ(r, k + 1) : mk_cx<R>(zero, zero);
+                        while (i < count && ops[i].op == ZOP_REFL && ops[i].k == k) {
+                            const C tau1 = mk_cx<R>(ops[i].a[0], ops[i].a[1]);
+                            const C v2 = mk_cx<R>(ops[i].a[2], ops[i].a[3]);
+                            const C v2c = cconj(v2);
+                            const R tau2 = (tau1 * v2).re;
+                            const C zp = (rv && k + 2 <= n) ? ZZ(r, k + 2) : mk_cx<R>(zero, zero);   // prefetch
+                            if (rv) {
+                                const C z1 = zn;
+                                const C ss = e_axty<true>(tau1, z0, tau2, z1);
+                                ZZ(r, k) = z0 - ss;
+                                z0 = e_bsv<true>(z1, ss, v2c);
+                                zn = zp;
+                            }
+                            k += 1;
+                            i += 1;
+                        }
+                        if (rv) ZZ(r, k) = z0;
+                    } else {   // ZOP_SCALE
+                        const C t = mk_cx<R>(ops[i].a[0], ops[i].a[1]);
+                        if (rv)
+                            for (int j = ops[i].k; j <= ops[i].k2; ++j) ZZ(r, j) = ZZ(r, j) * t;
                         i += 1;
                     }
                 } else if constexpr (CPLX) {
@@ -1969,7 +2004,7 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
                     }
                 }
             }
-            named_bar_arrive<RB>(BAR_EMPTY0 + b);
+            named_bar_arrive<RB, RING_THREADS>(BAR_EMPTY0 + b);
             if (end) break;
         }
     }
@@ -1986,8 +2021,9 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
 // in registers — must not leak into the H-warp's step loop, which is compiled at the same per-thread register cap.
 template <class T, int CPL>
 __device__ __noinline__ void z_consumer_entry(int n, int lane, int ldz, T* Z, typename FastSolver<T, CPL>::ZOp* ring,
-                                              zring_hdr* hdr, int cap) {
+                                              zring_hdr* hdr, int cap, int zslot = 0) {
     FastSolver<T, CPL> F;
+    F.zslot = zslot;
     F.n = n;
     F.lane = lane;
     F.ldz = ldz;
@@ -2028,9 +2064,9 @@ template <class T, int CPL> struct qr_min_blocks {
                                  : 1;
 };
 
-// threads per CTA: the H-warp and the Z-warp, plus the helper H-warps of the complex double-double kernel at CPL = 3
+// threads per CTA: the H-warp and the Z-warp; the complex double-double kernel at CPL = 3 has three of each
 template <class T, int CPL> struct qr_threads {
-    static constexpr int value = 64 + 32 * (FastSolver<T, CPL>::NH - 1);
+    static constexpr int value = 32 * (FastSolver<T, CPL>::NH + FastSolver<T, CPL>::NZW);
 };
 
 template <class T, int CPL>
@@ -2063,7 +2099,7 @@ __global__ void __launch_bounds__((qr_threads<T, CPL>::value), (qr_min_blocks<T,
             s_w0 = w;
         }
         __syncthreads();
-        warp ^= (int)((s_w0 >> 2) & 1u);   // role index: 0 = H-warp, 1 = Z-warp (2, 3: helper H-warps, interchangeable)
+        warp ^= (int)((s_w0 >> 2) & 1u);   // role index: 0 = H-warp, 1 = Z-warp (2, 3: helper H-warps; 4, 5: more Z-warps: interchangeable)
     }
 
     FS F;
@@ -2126,9 +2162,13 @@ __global__ void __launch_bounds__((qr_threads<T, CPL>::value), (qr_min_blocks<T,
                     s_stats[3] = st[3];
                 }
             } else if (warp == 1) {
-                if (wantZ) z_consumer_entry<T, CPL>(n, lane, F.ldz, F.Z, F.ring, F.hdr, F.cap);
+                if (wantZ) z_consumer_entry<T, CPL>(n, lane, F.ldz, F.Z, F.ring, F.hdr, F.cap, 0);
             } else {
-                if constexpr (FS::NH > 1) F.helper_loop(warp - 1);
+                if constexpr (FS::NH > 1) {
+                    // roles 2 .. NH: helper H-warps (slots 1 .. NH-1); roles NH+1 .. : Z-warps (slots 1 .. NH-1)
+                    if (warp <= FS::NH) F.helper_loop(warp - 1);
+                    else if (wantZ) z_consumer_entry<T, CPL>(n, lane, F.ldz, F.Z, F.ring, F.hdr, F.cap, warp - FS::NH);
+                }
             }
             __syncthreads();
             info = s_info;
