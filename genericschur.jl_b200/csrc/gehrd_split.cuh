@@ -72,12 +72,13 @@ template <class T, int NMAX> struct GehrdSplit {
             T a[K];
             T acc = e_zero<T>();
             T head = e_zero<T>();
-            if (!HEADZERO) head = col[-1];
+            // (lanes past the last column load nothing: they would read a column another group is writing in this pass)
+            if (!HEADZERO && on) head = col[-1];
 #pragma unroll
             for (int t = 0; t < K; ++t) {
                 const int e = q + G * t;
                 a[t] = e_zero<T>();
-                if (e < nv) a[t] = col[e];
+                if (e < nv && on) a[t] = col[e];
                 acc = e_fma_cja(v[t], a[t], acc);
             }
 #pragma unroll
@@ -111,12 +112,13 @@ template <class T, int NMAX> struct GehrdSplit {
             T* row = H + ((on ? r : 1) - 1) + (size_t)c0 * ld;   // row[e ld] = H(r, c0+1+e), row[-ld] = H(r, c0)
             T a[K];
             T acc = e_zero<T>();
-            const T head = row[-ld];
+            T head = e_zero<T>();
+            if (on) head = row[-ld];
 #pragma unroll
             for (int t = 0; t < K; ++t) {
                 const int e = q + G * t;
                 a[t] = e_zero<T>();
-                if (e < nv) a[t] = row[(size_t)e * ld];
+                if (e < nv && on) a[t] = row[(size_t)e * ld];
                 acc = e_fma(a[t], v[t], acc);
             }
 #pragma unroll
