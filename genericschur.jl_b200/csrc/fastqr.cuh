@@ -496,8 +496,8 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
                 hbar();
                 if (driver) {
                     C t = mk_cx<R>(one, zero) - tau1;
-                    R at = c_abs(t);
-                    t = mk_cx<R>(t.re / at, t.im / at);
+                    const R rat = q_rcp(c_abs_q(t));
+                    t = mk_cx<R>(t.re * rat, t.im * rat);
                     const C tc = cconj(t);
                     if (lane == 0) {
                         HH(k0 + 1, k0) = HH(k0 + 1, k0) * tc;
@@ -555,9 +555,9 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
                 C h11 = HH(mm, mm), h22 = HH(mm + 1, mm + 1);
                 C h11s = h11 - shift;
                 R h21 = HH(mm + 1, mm).re;
-                R s = abs1(h11s) + r_abs(h21);
-                h11s = mk_cx<R>(h11s.re / s, h11s.im / s);
-                h21 = h21 / s;
+                const R rs = q_rcp(abs1(h11s) + r_abs(h21));
+                h11s = mk_cx<R>(h11s.re * rs, h11s.im * rs);
+                h21 = h21 * rs;
                 R h10 = HH(mm, mm - 1).re;
                 hit = r_abs(h10) * r_abs(h21) <= ulp * (abs1(h11s) * (abs1(h11) + abs1(h22)));
             }
@@ -570,9 +570,9 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
         {
             C h11s = HH(k0, k0) - shift;
             R h21 = HH(k0 + 1, k0).re;
-            R s = abs1(h11s) + r_abs(h21);
-            v0 = mk_cx<R>(h11s.re / s, h11s.im / s);
-            v1 = mk_cx<R>(h21 / s, zero);
+            const R rs = q_rcp(abs1(h11s) + r_abs(h21));
+            v0 = mk_cx<R>(h11s.re * rs, h11s.im * rs);
+            v1 = mk_cx<R>(h21 * rs, zero);
         }
         reserve_ops(iend - k0 + 4);
         if constexpr (NH > 1) {
@@ -712,8 +712,9 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
         const R zero = r_const<R>(0.0);
         C t = HH(iend, iend - 1);
         if (t.im != zero) {
-            R rt = c_abs(t);
-            t = mk_cx<R>(t.re / rt, t.im / rt);
+            R rt = c_abs_q(t);
+            const R rrt = q_rcp(rt);
+            t = mk_cx<R>(t.re * rrt, t.im * rrt);
             const C tc = cconj(t);
             for (int c = iend + 1 + lane; c <= n; c += 32) HH(iend, c) = HH(iend, c) * tc;
             for (int r = 1 + lane; r <= iend - 1; r += 32) HH(r, iend) = HH(r, iend) * t;

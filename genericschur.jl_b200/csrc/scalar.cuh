@@ -238,7 +238,7 @@ GS_DEV bool q_exp_in(double a, unsigned lo, unsigned hi) {   // biased exponent 
     return (e - lo) <= (hi - lo);
 }
 GS_DEV double q_rcp(double a) { return q_exp_in(a, 40u, 2000u) ? fast_rcp(a) : 1.0 / a; }
-GS_DEV dd_t q_rcp(const dd_t& a) { return mk_dd(1.0) / a; }
+GS_DEV dd_t q_rcp(const dd_t& a) { return q_exp_in(a.hi, 1023u - 300u, 1023u + 300u) ? dd_rcp_fast(a) : mk_dd(1.0) / a; }
 GS_DEV double q_sqrt(double a) { return (a > 0.0 && q_exp_in(a, 40u, 2000u)) ? fast_sqrt(a) : __dsqrt_rn(a); }
 GS_DEV dd_t q_sqrt(const dd_t& a) { return dd_sqrt(a); }
 
@@ -341,20 +341,45 @@ GS_DEV cx<double> c_sqrt_q(const cx<double>& z) {
     }
     return mk_cx<double>(xi, eta);
 }
-GS_DEV cx<dd_t> c_sqrt_q(const cx<dd_t>& z) { return c_sqrt(z); }
+// double-double: |z| and rho from reciprocal square roots (no division: eta = y / (2 rho) = y rsqrt(rho^2) / 2)
+GS_DEV cx<dd_t> c_sqrt_q(const cx<dd_t>& z) {
+    const double m = fmax(fabs(z.re.hi), fabs(z.im.hi));
+    if (!q_exp_in(m, 1023u - 300u, 1023u + 300u)) return c_sqrt(z);   // also zero / inf / nan
+    const dd_t q = z.re * z.re + z.im * z.im;
+    const dd_t h = q * dd_rsqrt_fast(q);
+    const dd_t q2 = dd_mul_d(h + r_abs(z.re), 0.5);
+    const dd_t rs2 = dd_rsqrt_fast(q2);
+    const dd_t rho = q2 * rs2;
+    dd_t xi = rho, eta = dd_mul_d(z.im * rs2, 0.5);
+    if (z.re.hi < 0.0) {
+        xi = r_abs(eta);
+        eta = r_copysign(rho, z.im);
+    }
+    return mk_cx<dd_t>(xi, eta);
+}
 GS_DEV cx<double> c_div_q(const cx<double>& a, const cx<double>& b) {
     const double m = fmax(fabs(b.re), fabs(b.im));
     if (!q_exp_in(m, 1023u - 400u, 1023u + 400u)) return a / b;
     const double rd = fast_rcp(fma(b.re, b.re, b.im * b.im));
     return mk_cx<double>(fma(a.re, b.re, a.im * b.im) * rd, fma(a.im, b.re, -a.re * b.im) * rd);
 }
-GS_DEV cx<dd_t> c_div_q(const cx<dd_t>& a, const cx<dd_t>& b) { return a / b; }
+GS_DEV cx<dd_t> c_div_q(const cx<dd_t>& a, const cx<dd_t>& b) {
+    const double m = fmax(fabs(b.re.hi), fabs(b.im.hi));
+    if (!q_exp_in(m, 1023u - 300u, 1023u + 300u)) return a / b;
+    const dd_t rd = dd_rcp_fast(b.re * b.re + b.im * b.im);
+    return mk_cx<dd_t>((a.re * b.re + a.im * b.im) * rd, (a.im * b.re - a.re * b.im) * rd);
+}
 GS_DEV double c_abs_q(const cx<double>& a) {
     const double m = fmax(fabs(a.re), fabs(a.im));
     if (!q_exp_in(m, 1023u - 400u, 1023u + 400u)) return c_abs(a);
     return fast_sqrt(fma(a.re, a.re, a.im * a.im));
 }
-GS_DEV dd_t c_abs_q(const cx<dd_t>& a) { return c_abs(a); }
+GS_DEV dd_t c_abs_q(const cx<dd_t>& a) {
+    const double m = fmax(fabs(a.re.hi), fabs(a.im.hi));
+    if (!q_exp_in(m, 1023u - 300u, 1023u + 300u)) return c_abs(a);
+    const dd_t q = a.re * a.re + a.im * a.im;
+    return q * dd_rsqrt_fast(q);
+}
 
 // element-type traits
 template <class T> struct etraits;
