@@ -435,6 +435,17 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
         this->prof_x[3] += tl0 - ty1;
 #endif
         int t = 0;
+        // The operands of block-L are fetched one step ahead (right after the barrier that publishes block-R of the previous
+        // step, next to the bulge loads), so their latency sits under the reflector chain; the entry H[k+1, k+2] that the far
+        // part of the previous step produces for the same lane comes from its carry register instead of shared memory.
+        C px0 = mk_cx<R>(0.0, 0.0), px1 = px0;
+        if (len > 0) {
+            uint32_t ba = ca[0] + ES * (uint32_t)kf;
+#pragma unroll
+            for (int s = 1; s < CPL; ++s) ba = ((unsigned)(jl[s] - kf) <= 1u) ? ca[s] + ES * (uint32_t)kf : ba;
+            px0 = lds_e<C>(ba);
+            px1 = lds_e<C>(ba + ES);
+        }
         for (;;) {
             if (t >= len) break;
             int chunk = len - t;
@@ -461,7 +472,7 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
                         ba = in ? ca[s] + kb : ba;
                         pL = pL || in;
                     }
-                    const C x0 = lds_e<C>(ba), x1 = lds_e<C>(ba + ES);
+                    const C x0 = px0, x1 = px1;
                     const C ss = mk_cx<R>(fma(tau1.re, x0.re, fma(tau1.im, x0.im, tau2 * x1.re)),
                                           fma(tau1.re, x0.im, fma(-tau1.im, x0.re, tau2 * x1.im)));
                     sts_c64_if(ba, x0 - ss, pL);
@@ -516,6 +527,13 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
                 // ---- the bulge: H[k+1, k] (complex), H[k+2, k] (real) ----
                 nv0 = lds_e<C>(ak + kb + ES);
                 nv1 = lds_e<R>(ak + kb + 2 * ES);
+                {   // block-L operands of step k+1: column j in {k+1, k+2}, rows k+1, k+2
+                    uint32_t bn = ca[0] + kb + ES;
+#pragma unroll
+                    for (int s = 1; s < CPL; ++s) bn = ((unsigned)(jl[s] - k - 1) <= 1u) ? ca[s] + kb + ES : bn;
+                    px0 = lds_e<C>(bn);
+                    px1 = lds_e<C>(bn + ES);
+                }
                 const C otau1 = tau1, ov2 = v2;
                 const R otau2 = tau2;
                 // ---- reflector k+1 (src/householder.jl:56-102) from (nv0, nv1): beta = -sign(Re a) ||.||,
@@ -554,7 +572,11 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
                     sv.im = flip_if(sv.im, sg[s]);
                     c[s] = e_fnma(ss, ov2, y[s]);
                     sts_c64_if(sa[s], sv, act[s]);
-                    sts_c64_if(sa[s] + ES, c[s], jl[s] == k + 2);  // H[k+1, k+2] enters the block next step
+                    // H[k+1, k+2] enters the block next step: handed to block-L in a register (its shared-memory copy is
+                    // rewritten by block-L of step k+1 or, after the last step, by the sweep's write-back of the carries)
+                    const bool own2 = jl[s] == k + 2;
+                    px0.re = own2 ? c[s].re : px0.re;
+                    px0.im = own2 ? c[s].im : px0.im;
                 }
                 ak = ak1;
             }
