@@ -3,6 +3,7 @@
 //   gschur_cuda_large            : + windowed multi-bulge QR iteration with DMMA GEMM updates (large_qr.cuh)
 #include <cmath>
 #include <cstring>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -40,6 +41,16 @@ extern "C" const char* gschur_cuda_large_last_error(void) { return l_err.c_str()
         }                                                                        \
     } while (0)
 
+// frees what an entry point allocated on every way out (the error returns of L_TRY included)
+namespace {
+struct OnExit {
+    std::function<void()> f;
+    ~OnExit() {
+        if (f) f();
+    }
+};
+}  // namespace
+
 extern "C" int gschur_cuda_hessenberg_large(int n, double* A, int lda, double* tau, double* Q, int ldq, uint32_t flags) {
     l_err.clear();
     if (n < 0 || lda < n || (Q && ldq < n) || !A) {
@@ -57,7 +68,17 @@ extern "C" int gschur_cuda_hessenberg_large(int n, double* A, int lda, double* t
     const bool dev = (flags & GSCHUR_FLAG_DEVICE_PTRS) != 0;
     const size_t nn = (size_t)n * n;
     double *dA = nullptr, *dQ = nullptr;
-    if (dev && lda == n && (!Q || ldq == n)) {
+    const bool inplace = dev && lda == n && (!Q || ldq == n);
+    LargeWork w{};
+    OnExit cleanup{[&] {
+        lg_free(w, s);
+        if (!inplace) {
+            cudaStreamSynchronize(s);
+            if (dA) cudaFree(dA);
+            if (dQ) cudaFree(dQ);
+        }
+    }};
+    if (inplace) {
         dA = A;
         dQ = Q;
     } else {
@@ -65,7 +86,6 @@ extern "C" int gschur_cuda_hessenberg_large(int n, double* A, int lda, double* t
         L_TRY(cudaMemcpy2DAsync(dA, (size_t)n * 8, A, (size_t)lda * 8, (size_t)n * 8, n, cudaMemcpyDefault, s));
         if (Q) L_TRY(cudaMallocAsync((void**)&dQ, nn * sizeof(double), s));
     }
-    LargeWork w{};
     std::string err;
     int rc = lg_alloc(w, n, s, &err);
     w.A = dA;
@@ -75,16 +95,11 @@ extern "C" int gschur_cuda_hessenberg_large(int n, double* A, int lda, double* t
         return rc;
     }
     if (tau && n > 1) L_TRY(cudaMemcpyAsync(tau, w.tau, (size_t)(n - 1) * 8, cudaMemcpyDefault, s));
-    if (dA != A) {
+    if (!inplace) {
         L_TRY(cudaMemcpy2DAsync(A, (size_t)lda * 8, dA, (size_t)n * 8, (size_t)n * 8, n, cudaMemcpyDefault, s));
         if (Q) L_TRY(cudaMemcpy2DAsync(Q, (size_t)ldq * 8, dQ, (size_t)n * 8, (size_t)n * 8, n, cudaMemcpyDefault, s));
     }
-    lg_free(w, s);
     L_TRY(cudaStreamSynchronize(s));
-    if (dA != A) {
-        cudaFree(dA);
-        if (dQ) cudaFree(dQ);
-    }
     return 0;
 }
 
@@ -138,6 +153,14 @@ extern "C" int gschur_cuda_large(int n, double* A, int lda, double* Z, int ldz, 
     const size_t nn = (size_t)n * n;
     double *dA = nullptr, *dZ = nullptr, *dw = nullptr;
     const bool inplace = dev && lda == n && (!Z || ldz == n);
+    OnExit cleanup{[&] {
+        if (!inplace) {
+            cudaStreamSynchronize(s);
+            if (dA) cudaFree(dA);
+            if (dZ) cudaFree(dZ);
+            if (dw) cudaFree(dw);
+        }
+    }};
     if (inplace) {
         dA = A;
         dZ = Z;
@@ -202,11 +225,6 @@ extern "C" int gschur_cuda_large(int n, double* A, int lda, double* Z, int ldz, 
         L_TRY(cudaMemcpyAsync(w, dw, (size_t)2 * n * 8, cudaMemcpyDefault, s));
     }
     L_TRY(cudaStreamSynchronize(s));
-    if (!inplace) {
-        cudaFree(dA);
-        if (dZ) cudaFree(dZ);
-        cudaFree(dw);
-    }
     if (info) *info = qinfo;
     if (stats3) {
         stats3[0] = st.sweeps;

@@ -386,6 +386,27 @@ inline void lq_copy(cudaStream_t s, const double* src, int lds, double* dst, int
     note_launch();
 }
 
+// streams, events and scratch of one lg_qr call: released on every way out (the error returns of LG_TRY included)
+struct LqResources {
+    cudaStream_t caller = nullptr;
+    cudaStream_t* sA = nullptr;
+    cudaStream_t* sB = nullptr;
+    cudaEvent_t* evA = nullptr;
+    cudaEvent_t* evB = nullptr;
+    double** base = nullptr;
+    ~LqResources() {
+        if (sA && *sA) cudaStreamSynchronize(*sA);
+        if (sB && *sB) cudaStreamSynchronize(*sB);
+        for (int q = 0; q < 2; ++q) {
+            if (evA && evA[q]) cudaEventDestroy(evA[q]);
+            if (evB && evB[q]) cudaEventDestroy(evB[q]);
+        }
+        if (sB && *sB) cudaStreamDestroy(*sB);
+        if (sA && *sA) cudaStreamDestroy(*sA);
+        if (base && *base) cudaFreeAsync(*base, caller);
+    }
+};
+
 struct LargeQrStats {
     long sweeps = 0, windows = 0, small_blocks = 0;
 };
@@ -395,6 +416,15 @@ struct LargeQrStats {
 inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::string* err, LargeQrStats* stats) {
     const size_t wbuf = (size_t)LQ_SMALL * std::max(n, LQ_SMALL);
     double* base = nullptr;
+    cudaStream_t sB = nullptr, sA = nullptr;
+    cudaEvent_t evChase[2] = {nullptr, nullptr}, evFar[2] = {nullptr, nullptr};
+    LqResources res;
+    res.caller = s;
+    res.sA = &sA;
+    res.sB = &sB;
+    res.evA = evChase;
+    res.evB = evFar;
+    res.base = &base;
     // scratch: U (LQ_SMALL^2), tmp (LQ_SMALL x n), blk (LQ_SMALL^2), zblk (LQ_SMALL^2), wblk, shifts, scan
     const size_t total = 5 * (size_t)LQ_SMALL * LQ_SMALL + wbuf + 2 * LQ_SMALL + 4 * LQ_NB * LQ_MAXC + 64 +
                          2 * (size_t)LQ_MAXC * LQ_W * LQ_W;
@@ -489,8 +519,6 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
     // second stream: the far updates of window t run while window t+1 is being chased
     // The chase kernel needs a whole SM (198 KB of shared memory): its stream gets the highest priority so that the
     // block scheduler hands it the first SM the concurrently running GEMMs vacate.
-    cudaStream_t sB = nullptr, sA = nullptr;
-    cudaEvent_t evChase[2] = {nullptr, nullptr}, evFar[2] = {nullptr, nullptr};
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     LG_TRY(cudaStreamCreateWithPriority(&sB, cudaStreamNonBlocking, prio_lo));
@@ -539,7 +567,7 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
             lq_eye_kernel<<<(nw * nw + 255) / 256, 256, 0, s>>>(dZb, nw, nw);
             note_launch();
             int rc = run_small(dBlk, nw, dZb, dWb, true);
-            if (rc) { cudaFreeAsync(base, s); return -2; }
+            if (rc) return -2;
             int hinfo = 0;
             LG_TRY(cudaMemcpyAsync(&hinfo, dInfo, sizeof(int), cudaMemcpyDeviceToHost, s));
             LG_TRY(cudaStreamSynchronize(s));
@@ -547,7 +575,7 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
             lq_copy(s, dBlk, nw, H + (size_t)(istart - 1) + (size_t)(istart - 1) * n, n, nw, nw);
             if (nw > 1) {
                 rc = apply_outside(dZb, nw, istart, iend);
-                if (rc) { cudaFreeAsync(base, s); return rc; }
+                if (rc) return rc;
             }
             if (stats) stats->small_blocks += 1;
             t_small += now() - t0;
@@ -577,7 +605,7 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
             }
         } else {
             int rc = run_small(dBlk, ns, nullptr, dWb, false);
-            if (rc) { cudaFreeAsync(base, s); return -2; }
+            if (rc) return -2;
             LG_TRY(cudaMemcpyAsync(hshift.data(), dWb, sizeof(double) * 2 * ns, cudaMemcpyDeviceToHost, s));
             LG_TRY(cudaStreamSynchronize(s));
         }
@@ -635,7 +663,7 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
                 if (pmax < 0) continue;
                 wn.wlo[c] = std::max(L, pmin - 1);
                 wn.whi[c] = std::min(I, pmax + 3);
-                if (wn.whi[c] - wn.wlo[c] + 1 > LQ_W) { *err = "internal: chase window too large"; cudaFreeAsync(base, s); return -2; }
+                if (wn.whi[c] - wn.wlo[c] + 1 > LQ_W) { *err = "internal: chase window too large"; return -2; }
                 any = true;
             }
             if (any) wins.push_back(wn);
@@ -708,16 +736,9 @@ inline int lg_qr(double* H, double* Z, int n, double* w, cudaStream_t s, std::st
     }
     if (dbg_time) fprintf(stderr, "[lg_qr] scan+sync %.3f s, small blocks %.3f s, shifts %.3f s, window enqueue %.3f s\n", t_scan, t_small, t_shift, t_enq);
     LG_TRY(cudaStreamSynchronize(s));
-    cudaStreamSynchronize(sB);
-    cudaStreamDestroy(sB);
-    cudaStreamDestroy(sA);
+    LG_TRY(cudaStreamSynchronize(sB));
     s = s_caller;
-    for (int q = 0; q < 2; ++q) {
-        cudaEventDestroy(evChase[q]);
-        cudaEventDestroy(evFar[q]);
-    }
-    cudaFreeAsync(base, s);
-    return rc_final;
+    return rc_final;   // `res` destroys the streams and events and returns the scratch to the pool
 }
 
 }  // namespace gs
