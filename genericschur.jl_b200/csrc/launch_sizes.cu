@@ -10,13 +10,19 @@ unsigned long long launch_counter() { return g_launch_counter.load(); }
 
 // Per-stage timing of the batched paths: CUDA events on the launching stream, one group of four marks per
 // (sub-)batch — before stage A, after A, after B, after C (+ redo) — summed over the groups of the most recent call.
-// Development / bench aid: single caller at a time (guarded by a mutex, events created on the calling device).
+// Development / bench aid: single caller at a time (guarded by a mutex); the events belong to the device that was current
+// when timing was switched on, and launches on any other device (the multi-device host path) are not marked.
 static bool g_stage_timing = false;
+static int g_stage_dev = -1;
 static std::mutex g_ev_mu;
 struct MarkGroup { cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr}; };
 static std::vector<MarkGroup> g_marks;
 static size_t g_marks_used = 0;
-void stage_timing_enable(bool on) { g_stage_timing = on; }
+void stage_timing_enable(bool on) {
+    g_stage_timing = on;
+    g_stage_dev = -1;
+    if (on) cudaGetDevice(&g_stage_dev);
+}
 bool stage_timing_enabled() { return g_stage_timing; }
 void stage_timing_begin_call() {
     if (!g_stage_timing) return;
@@ -25,6 +31,8 @@ void stage_timing_begin_call() {
 }
 void stage_timing_mark(int which, cudaStream_t s) {
     if (!g_stage_timing || which < 0 || which > 3) return;
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev != g_stage_dev) return;
     std::lock_guard<std::mutex> lk(g_ev_mu);
     if (which == 0) {
         if (g_marks_used == g_marks.size()) g_marks.emplace_back();
