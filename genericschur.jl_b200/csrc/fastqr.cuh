@@ -41,6 +41,12 @@
 #define GS_ZRUN 8
 #endif
 
+// smallest CPL (columns per lane) at which the complex double-double kernel uses several H- and Z-warps per matrix
+// (measured at 64x64, CPL = 2: 6890 matrices/s with two of each against 7176 with one — several CTAs share an SM there)
+#ifndef GS_CDD_NH_MINCPL
+#define GS_CDD_NH_MINCPL 3
+#endif
+
 namespace gs {
 
 enum { ZOP_REFL = 1, ZOP_SCALE = 2, ZOP_REFL3 = 3, ZOP_REFL2 = 4, ZOP_GIVENS = 5 };
@@ -197,7 +203,7 @@ template <class T, int CPL, bool LOG = false> struct FastSolver {
     // Complex double-double at CPL = 3 (65 <= n <= 96): the three columns / rows a lane owns go to three H-warps — the
     // driver (slot 0: everything the single H-warp did, for its own slot) and NH - 1 helpers that run the step loop of a
     // sweep for their slot and are parked at a barrier otherwise (see sweep_steps / helper_loop).
-    static constexpr int NH = (etraits<T>::is_complex && sizeof(R) == 16 && CPL == 3 && !LOG) ? CPL : 1;
+    static constexpr int NH = (etraits<T>::is_complex && sizeof(R) == 16 && CPL >= GS_CDD_NH_MINCPL && !LOG) ? CPL : 1;
     // ... and the three rows of Z a lane owns to NH Z-warps (all of them consume every record of the ring)
     static constexpr int NZW = NH;
     static constexpr int RING_THREADS = 32 * (1 + NZW);   // the driver and the Z-warps meet at the ring's named barriers

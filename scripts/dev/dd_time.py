@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import torch
 from __graft_entry__ import load_package
 gs = load_package()
-for kind, n, batch in ((gs.CDD, 96, 592), (gs.DD, 96, 592), (gs.CDD, 32, 2048)):
+for kind, n, batch in ((gs.CDD, 96, 592), (gs.DD, 96, 592), (gs.CDD, 64, 592), (gs.CDD, 32, 2048)):
     lead = 4 if kind == gs.CDD else 2
     hi = torch.rand((batch, n, n, lead), dtype=torch.float64, device="cuda")
     if lead == 4:
