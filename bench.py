@@ -517,6 +517,9 @@ def measure_workload(gs, torch, dist, args, name, world, rank, local_rank, with_
         }
         if roofline["qr_total"]["achieved"]:
             roofline["qr_total"]["frac"] = roofline["qr_total"]["achieved"] / fp64_peak
+            roofline["qr_total"]["note"] = ("stages B + C against the QR share of the flops (sweeps on H and on Z): the figure to set beside "
+                                            "round 1's roofline.frac, which was the fused QR kernel against the same flops; roofline.frac itself "
+                                            "now is stage B (the dominant kernel) against the H sweeps only")
         rec["roofline"] = roofline
     del A0, A, Z, w, info, stats
     torch.cuda.empty_cache()
