@@ -462,8 +462,13 @@ int run_slice(const HostJob& J, int dev, int64_t b0, int64_t b1, std::string* er
         SL_TRY(grow(buf[i].dinfo, buf[i].capn, sizeof(int32_t) * chunk));
         SL_TRY(grow(buf[i].dstats, buf[i].capst, sizeof(uint32_t) * GSCHUR_STATS_PER_MATRIX * chunk));
         if (staged) {
-            SL_TRY(grow_pinned(buf[i].hA, buf[i].hcapA, mat * chunk));
-            if (wantZ) SL_TRY(grow_pinned(buf[i].hZ, buf[i].hcapZ, mat * chunk));
+            // no page-locked memory to be had: leave the staging to the driver (slower, not an error)
+            cudaError_t eh = grow_pinned(buf[i].hA, buf[i].hcapA, mat * chunk);
+            if (eh == cudaSuccess && wantZ) eh = grow_pinned(buf[i].hZ, buf[i].hcapZ, mat * chunk);
+            if (eh != cudaSuccess) {
+                cudaGetLastError();
+                staged = false;
+            }
         }
     }
     {
