@@ -22,6 +22,7 @@
 // The arithmetic per entry is the reference's (src/GenericSchur.jl:877-946 real, :426-460 complex); every entry sees
 // the same operations in the same order.
 #pragma once
+#include <type_traits>
 #include "chainqr.cuh"
 
 namespace gs {
@@ -120,6 +121,27 @@ template <int CPL> struct OwnR : ChainR<32, CPL> {
             unsigned char* lp = lg.cur;
             bool ok = true;
             int i = 0;
+            // With two columns / rows per lane (n > 32) the slot of the high ones (j >= 33) is a plain column item of every lane
+            // while k <= KLO, the slot of the low ones (j <= 32) a plain row item once k >= KHI: the step loop is instantiated
+            // for the three regimes, and the constant roles drop out of two thirds of the steps (the kernel is issue bound).
+            constexpr int KLO = 29, KHI = 34;
+            int mode = 0;
+            if constexpr (CPL == 2) {
+                const int kc = mx + t;
+                if (kc <= KLO) {
+                    mode = 1;
+                    if (chunk > KLO - kc + 1) chunk = KLO - kc + 1;
+                } else if (kc >= KHI) {
+                    mode = 2;
+                } else if (chunk > KHI - kc) {
+                    chunk = KHI - kc;
+                }
+            }
+            auto steps = [&](auto MODE_) {
+            constexpr int MODE = decltype(MODE_)::value;
+            // slot s has a constant role in this regime: LO = column item (never in the block), HI = row item
+            auto is_lo = [](int s) { return MODE == 1 && s == CPL - 1; };
+            auto is_hi = [](int s) { return MODE == 2 && s == 0; };
 #pragma unroll 1
             for (; i < chunk && ok; ++i) {
                 const int k = mx + t + i;
@@ -129,11 +151,11 @@ template <int CPL> struct OwnR : ChainR<32, CPL> {
                 // ---- block-L: column j in k..k+2 (at most one of a lane's columns), rows k..k+2 ----
                 {
                     uint32_t ba = ca[0] + kb;
-                    bool pL = (unsigned)(jl[0] - k) <= 2u;
+                    bool pL = (is_lo(0) || is_hi(0)) ? false : ((unsigned)(jl[0] - k) <= 2u);
 #pragma unroll
                     for (int s = 1; s < CPL; ++s) {
-                        const bool in = (unsigned)(jl[s] - k) <= 2u;
-                        ba = in ? ca[s] + kb : ba;
+                        const bool in = (is_lo(s) || is_hi(s)) ? false : ((unsigned)(jl[s] - k) <= 2u);
+                        ba = (is_hi(0) && s == 1) ? ca[s] + kb : (in ? ca[s] + kb : ba);
                         pL = pL || in;
                     }
                     const R x0 = lds_e<R>(ba), x1 = lds_e<R>(ba + ES), x2 = lds_e<R>(ba + 2 * ES);
@@ -149,22 +171,24 @@ template <int CPL> struct OwnR : ChainR<32, CPL> {
                 R y[CPL];
 #pragma unroll
                 for (int s = 0; s < CPL; ++s) {
-                    const bool isR = jr[s] <= k - 1;
-                    act[s] = isR || (jl[s] >= k + 3);
+                    const bool isR = is_lo(s) ? false : (is_hi(s) ? true : (jr[s] <= k - 1));
+                    act[s] = is_lo(s) ? (jl[s] > 0) : (is_hi(s) ? true : (isR || (jl[s] >= k + 3)));
                     sa[s] = isR ? ak + ib[s] : ca[s] + kb;
                     const uint32_t ya = isR ? ak2 + ib[s] : sa[s] + 2 * ES;
-                    lds_f64_if(c1[s], sa[s], jr[s] == k - 1);
-                    lds_f64_if(c2[s], ak1 + ib[s], jr[s] == k - 1);
+                    if (!is_lo(s) && !is_hi(s)) {
+                        lds_f64_if(c1[s], sa[s], jr[s] == k - 1);
+                        lds_f64_if(c2[s], ak1 + ib[s], jr[s] == k - 1);
+                    }
                     y[s] = lds_e<R>(ya);
                 }
                 // ---- block-R: row i in k..min(k+3, iend) (at most one of a lane's rows), columns k..k+2 ----
                 {
                     uint32_t ro = ib[0];
-                    bool pR = (unsigned)(jr[0] - k) <= 3u && jr[0] <= iend;
+                    bool pR = (is_lo(0) || is_hi(0)) ? false : ((unsigned)(jr[0] - k) <= 3u && jr[0] <= iend);
 #pragma unroll
                     for (int s = 1; s < CPL; ++s) {
-                        const bool in = (unsigned)(jr[s] - k) <= 3u && jr[s] <= iend;
-                        ro = in ? ib[s] : ro;
+                        const bool in = (is_lo(s) || is_hi(s)) ? false : ((unsigned)(jr[s] - k) <= 3u && jr[s] <= iend);
+                        ro = (is_hi(0) && s == 1) ? ib[s] : (in ? ib[s] : ro);
                         pR = pR || in;
                     }
                     const R y0 = lds_e<R>(ak + ro), y1 = lds_e<R>(ak1 + ro), y2 = lds_e<R>(ak2 + ro);
@@ -222,12 +246,18 @@ template <int CPL> struct OwnR : ChainR<32, CPL> {
                     c1[s] = fma(-ss, otau2, c2[s]);
                     c2[s] = fma(-ss, otau3, y[s]);
                     sts_f64_if(sa[s], sv, act[s]);
-                    const bool own3 = jl[s] == k + 3;          // column k+3 enters the block next step
-                    sts_f64_if(sa[s] + ES, c1[s], own3);
-                    sts_f64_if(sa[s] + 2 * ES, c2[s], own3);
+                    if (!is_lo(s) && !is_hi(s)) {
+                        const bool own3 = jl[s] == k + 3;      // column k+3 enters the block next step
+                        sts_f64_if(sa[s] + ES, c1[s], own3);
+                        sts_f64_if(sa[s] + 2 * ES, c2[s], own3);
+                    }
                 }
                 ak = ak1;
             }
+            };
+            if (mode == 1) steps(std::integral_constant<int, 1>{});
+            else if (mode == 2) steps(std::integral_constant<int, 2>{});
+            else steps(std::integral_constant<int, 0>{});
             if (lg.on && !lg.ovf) {
                 lg.cur += 32 * i;
                 lg.left -= i;
@@ -457,6 +487,25 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
             unsigned char* lp = lg.cur;
             bool ok = true;
             int i = 0;
+            // three instances of the step loop by the regime of k (see OwnR::sweep): the slot of the high columns / rows is a
+            // plain column item while k <= KLO, the slot of the low ones a plain row item once k >= KHI
+            constexpr int KLO = 30, KHI = 34;
+            int mode = 0;
+            if constexpr (CPL == 2) {
+                const int kc = kf + t;
+                if (kc <= KLO) {
+                    mode = 1;
+                    if (chunk > KLO - kc + 1) chunk = KLO - kc + 1;
+                } else if (kc >= KHI) {
+                    mode = 2;
+                } else if (chunk > KHI - kc) {
+                    chunk = KHI - kc;
+                }
+            }
+            auto steps = [&](auto MODE_) {
+            constexpr int MODE = decltype(MODE_)::value;
+            auto is_lo = [](int s) { return MODE == 1 && s == CPL - 1; };
+            auto is_hi = [](int s) { return MODE == 2 && s == 0; };
 #pragma unroll 1
             for (; i < chunk && ok; ++i) {
                 const int k = kf + t + i;
@@ -465,11 +514,11 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
                 // ---- block-L: column j in {k, k+1} (at most one of a lane's columns), rows k, k+1 ----
                 {
                     uint32_t ba = ca[0] + kb;
-                    bool pL = (unsigned)(jl[0] - k) <= 1u;
+                    bool pL = (is_lo(0) || is_hi(0)) ? false : ((unsigned)(jl[0] - k) <= 1u);
 #pragma unroll
                     for (int s = 1; s < CPL; ++s) {
-                        const bool in = (unsigned)(jl[s] - k) <= 1u;
-                        ba = in ? ca[s] + kb : ba;
+                        const bool in = (is_lo(s) || is_hi(s)) ? false : ((unsigned)(jl[s] - k) <= 1u);
+                        ba = (is_hi(0) && s == 1) ? ca[s] + kb : (in ? ca[s] + kb : ba);
                         pL = pL || in;
                     }
                     const C x0 = px0, x1 = px1;
@@ -487,25 +536,27 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
                 C y[CPL];
 #pragma unroll
                 for (int s = 0; s < CPL; ++s) {
-                    const bool isR = jr[s] <= k - 1;
-                    act[s] = isR || (jl[s] >= k + 2);
+                    const bool isR = is_lo(s) ? false : (is_hi(s) ? true : (jr[s] <= k - 1));
+                    act[s] = is_lo(s) ? (jl[s] > 0) : (is_hi(s) ? true : (isR || (jl[s] >= k + 2)));
                     sa[s] = isR ? ak + ib[s] : ca[s] + kb;
                     const uint32_t ya = isR ? ak1 + ib[s] : sa[s] + ES;
                     sg[s] = isR ? 0x80000000u : 0u;
-                    const bool ent = jr[s] == k - 1;              // row k-1 left the block in the previous step
-                    lds_c64_if(c[s], sa[s], ent);
-                    c[s].im = flip_if(c[s].im, ent ? 0x80000000u : 0u);
+                    if (!is_lo(s) && !is_hi(s)) {
+                        const bool ent = jr[s] == k - 1;          // row k-1 left the block in the previous step
+                        lds_c64_if(c[s], sa[s], ent);
+                        c[s].im = flip_if(c[s].im, ent ? 0x80000000u : 0u);
+                    }
                     y[s] = lds_e<C>(ya);
-                    y[s].im = flip_if(y[s].im, sg[s]);
+                    if (!is_lo(s)) y[s].im = flip_if(y[s].im, sg[s]);
                 }
                 // ---- block-R: row i in k..min(k+2, iend) (at most one of a lane's rows), columns k, k+1 ----
                 {
                     uint32_t ro = ib[0];
-                    bool pR = (unsigned)(jr[0] - k) <= 2u && jr[0] <= iend;
+                    bool pR = (is_lo(0) || is_hi(0)) ? false : ((unsigned)(jr[0] - k) <= 2u && jr[0] <= iend);
 #pragma unroll
                     for (int s = 1; s < CPL; ++s) {
-                        const bool in = (unsigned)(jr[s] - k) <= 2u && jr[s] <= iend;
-                        ro = in ? ib[s] : ro;
+                        const bool in = (is_lo(s) || is_hi(s)) ? false : ((unsigned)(jr[s] - k) <= 2u && jr[s] <= iend);
+                        ro = (is_hi(0) && s == 1) ? ib[s] : (in ? ib[s] : ro);
                         pR = pR || in;
                     }
                     const C y0 = lds_e<C>(ak + ro), y1 = lds_e<C>(ak1 + ro);
@@ -530,7 +581,9 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
                 {   // block-L operands of step k+1: column j in {k+1, k+2}, rows k+1, k+2
                     uint32_t bn = ca[0] + kb + ES;
 #pragma unroll
-                    for (int s = 1; s < CPL; ++s) bn = ((unsigned)(jl[s] - k - 1) <= 1u) ? ca[s] + kb + ES : bn;
+                    for (int s = 1; s < CPL; ++s)
+                        bn = (is_hi(0) && s == 1) ? ca[s] + kb + ES
+                                                  : ((!is_lo(s) && (unsigned)(jl[s] - k - 1) <= 1u) ? ca[s] + kb + ES : bn);
                     px0 = lds_e<C>(bn);
                     px1 = lds_e<C>(bn + ES);
                 }
@@ -569,17 +622,23 @@ template <int CPL> struct OwnC : ChainC<32, CPL> {
                     const C ss = mk_cx<R>(fma(otau1.re, x.re, fma(otau1.im, x.im, otau2 * y[s].re)),
                                           fma(otau1.re, x.im, fma(-otau1.im, x.re, otau2 * y[s].im)));
                     C sv = x - ss;
-                    sv.im = flip_if(sv.im, sg[s]);
+                    if (!is_lo(s)) sv.im = flip_if(sv.im, sg[s]);
                     c[s] = e_fnma(ss, ov2, y[s]);
                     sts_c64_if(sa[s], sv, act[s]);
                     // H[k+1, k+2] enters the block next step: handed to block-L in a register (its shared-memory copy is
                     // rewritten by block-L of step k+1 or, after the last step, by the sweep's write-back of the carries)
-                    const bool own2 = jl[s] == k + 2;
-                    px0.re = own2 ? c[s].re : px0.re;
-                    px0.im = own2 ? c[s].im : px0.im;
+                    if (!is_lo(s) && !is_hi(s)) {
+                        const bool own2 = jl[s] == k + 2;
+                        px0.re = own2 ? c[s].re : px0.re;
+                        px0.im = own2 ? c[s].im : px0.im;
+                    }
                 }
                 ak = ak1;
             }
+            };
+            if (mode == 1) steps(std::integral_constant<int, 1>{});
+            else if (mode == 2) steps(std::integral_constant<int, 2>{});
+            else steps(std::integral_constant<int, 0>{});
             if (lg.on && !lg.ovf) {
                 lg.cur += 32 * i;
                 lg.left -= i;
