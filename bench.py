@@ -57,6 +57,18 @@ class ClockSampler:
         self.gpu = gpu_index
         self.lines = []
         self.proc = None
+        self.first = 0
+
+    def wait_ready(self, timeout=3.0):
+        """Block until nvidia-smi has delivered its first sample: its start-up (NVML initialisation takes driver locks)
+        otherwise lands in the first timed step — measured: +10..50 ms on a 100 ms step."""
+        t0 = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t0 < timeout:
+            time.sleep(0.01)
+
+    def mark(self):
+        """Samples from here on belong to the timed region."""
+        self.first = len(self.lines)
 
     def start(self):
         try:
@@ -81,7 +93,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[self.first:] or self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -341,6 +353,8 @@ def measure_workload(gs, torch, dist, args, name, world, rank, local_rank, with_
         gs.gschur_device_(kind, n, batch, A.data_ptr(), Z.data_ptr(), w.data_ptr(), info.data_ptr(),
                           stats.data_ptr(), scale=True, stream=stream)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # started during the warm-up: see ClockSampler.wait_ready
     for _ in range(args.warmup):
         A.copy_(A0)
         step()
@@ -348,11 +362,11 @@ def measure_workload(gs, torch, dist, args, name, world, rank, local_rank, with_
     assert int((info != 0).sum().item()) == 0, "warm-up: some matrices did not converge"
     executed_units = stats[:, 1].to(torch.float64).mean().item()   # reflector applications per matrix (informative)
 
-    sampler = ClockSampler(local_rank)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = gs.launch_count()
+    sampler.wait_ready()
     barrier()
-    sampler.start()
+    sampler.mark()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):
         A.copy_(A0)                      # restore the input (untimed: outside the event pair)
